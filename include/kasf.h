@@ -1,0 +1,151 @@
+/*
+ * kasf.h -- C-ABI of libkasf.so: the B200 (sm_100a) implementation of the KASportsFormer
+ * inference forward pass (2D keypoint clips [B,T,17,3] -> 3D poses [B,T,17,3]) and of the
+ * MPJPE-family evaluation reduction.
+ *
+ * The reference (jw0r1n/KASportsFormer) has no native boundary: the path sits behind a Python
+ * class.  Each entry point below names the reference interface it replaces (file:line relative to
+ * the reference checkout).  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; every pointer marked "dev" is a CUDA device pointer owned by the caller
+ *     (the library never allocates or frees device memory and keeps no global mutable state);
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it and not synchronised;
+ *   - the caller selects the device (cudaSetDevice) before calling;
+ *   - return value: 0 on success, a negative KASF_E* code otherwise (kasf_strerror() names it);
+ *     CUDA launch errors are returned as -(1000 + cudaError_t);
+ *   - there is no CPU fallback: on a device that is not compute capability 10.x every compute
+ *     entry point returns KASF_EARCH.
+ */
+#ifndef KASF_H_
+#define KASF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KASF_VERSION 1
+
+#define KASF_OK        0
+#define KASF_EINVAL   -1   /* null pointer / bad enum / misaligned buffer                     */
+#define KASF_ESHAPE   -2   /* a shape this build does not implement (see kasf_config)         */
+#define KASF_EARCH    -3   /* current device is not sm_100                                     */
+#define KASF_ENOMEM   -4   /* caller-provided buffer too small                                 */
+
+/* Model hyper-parameters: the YAML model keys of the reference (configs/*.yaml:66-92) that reach
+ * KASportsFormer.__init__ (model/KASportsFormer.py:291-295).  This build implements
+ * dim_feat=128, num_heads=8, mlp_ratio=4, dim_rep=512, num_joints=17, dim_in=dim_out=3,
+ * neighbour_num=4, n_frames in [3,243]; anything else -> KASF_ESHAPE. */
+typedef struct kasf_config {
+    int32_t n_layers;
+    int32_t n_frames;
+    int32_t dim_feat;
+    int32_t dim_rep;
+    int32_t num_heads;
+    int32_t mlp_ratio;
+    int32_t num_joints;
+    int32_t neighbour_num;
+} kasf_config;
+
+/* FormerModule selectors (model/KASportsFormer.py:65-118) */
+#define KASF_KIND_ATTENTION 0   /* model/modules/selfattention.py      */
+#define KASF_KIND_GRAPH     1   /* model/modules/graph.py              */
+#define KASF_KIND_BONE      2   /* model/modules/bone_crossattention.py */
+#define KASF_MODE_SPATIAL   0
+#define KASF_MODE_TEMPORAL  1
+
+int         kasf_version(void);
+const char* kasf_strerror(int code);
+/* 0 if the current device can run this library, KASF_EARCH otherwise. */
+int         kasf_device_supported(void);
+
+/* ---- weights -------------------------------------------------------------------------------
+ * The "weight image" is one contiguous float32 array holding every floating-point tensor of the
+ * reference state_dict (names exactly as `KASportsFormer.state_dict()` produces them; the int64
+ * `num_batches_tracked` buffers are not part of it).  The library defines the order:
+ * kasf_weight_entry() enumerates (name, offset, numel).  Replaces: the nn.Module parameter tree
+ * built by model/KASportsFormer.py:291-318. */
+int    kasf_weight_entries(const kasf_config* cfg);
+int    kasf_weight_entry(const kasf_config* cfg, int index, char* name, size_t name_cap,
+                         size_t* offset_floats, size_t* numel);
+size_t kasf_weight_image_floats(const kasf_config* cfg);
+
+/* Pack the fp32 image (dev) into the kernel-ready blob (dev): bf16 tensor-core operand tiles in
+ * the 128B-swizzled K-major shared-memory layout, fp32 vectors, BatchNorm folded to scale/shift. */
+size_t kasf_packed_bytes(const kasf_config* cfg);
+int    kasf_pack_weights(const kasf_config* cfg, const float* image_dev, void* packed_dev,
+                         size_t packed_cap, void* stream);
+
+/* ---- forward -------------------------------------------------------------------------------
+ * Replaces KASportsFormer.forward (model/KASportsFormer.py:320-347).
+ *   x_dev   float32 [B, T, 17, 3] contiguous (x, y, confidence)
+ *   y_dev   float32 [B, T, 17, 3]            (3D pose, normalised units)
+ *   rep_dev float32 [B, T, 17, 512] or NULL  (`return_rep=True` output, :342-343)
+ *   ws_dev  scratch of at least kasf_workspace_bytes(cfg, B) bytes, 1024-byte aligned        */
+size_t kasf_workspace_bytes(const kasf_config* cfg, int B);
+int    kasf_forward(const kasf_config* cfg, const void* packed_dev, const float* x_dev,
+                    float* y_dev, float* rep_dev, int B, void* ws_dev, size_t ws_bytes,
+                    void* stream);
+/* Number of kernel launches one kasf_forward(B) enqueues (for bench accounting). */
+int    kasf_forward_launches(const kasf_config* cfg, int B);
+
+/* ---- per-stage entry points (used by the parity tests; same kernels kasf_forward runs) -------
+ * Kinematic anatomy features + the three embeddings.  Replaces bone_decomposer
+ * (model/KASportsFormer.py:42-62), BoneRefusion.forward (model/modules/bone_refusion.py:61-70,
+ * bone_MLP.py:16-27) and the embeddings (model/KASportsFormer.py:325-330).
+ *   bone_dev / limb_dev  float32 [B,T,17,3] or NULL (raw features, for tests)
+ *   X/XB/XL              float32 [B,T,17,128]                                                  */
+int kasf_kinematic_features(const kasf_config* cfg, const void* packed_dev, const float* x_dev,
+                            float* bone_dev, float* limb_dev, float* X_dev, float* XB_dev,
+                            float* XL_dev, int B, void* stream);
+
+/* One FormerModule (model/KASportsFormer.py:103-118): out = v + ls1*mixer(LN1(v)[,LN1_limb(XL)]);
+ * out = out + ls2*MLP(LN2(out)).  `layer` in [0,n_layers), kind/mode as above.
+ * in/out float32 [B,T,17,128] (may alias); XL_dev needed for KASF_KIND_BONE only. */
+int kasf_former_module(const kasf_config* cfg, const void* packed_dev, int layer, int kind,
+                       int mode, const float* in_dev, const float* XL_dev, float* out_dev, int B,
+                       void* stream);
+
+/* Adaptive fusion of the three branches (model/KASportsFormer.py:279-282). */
+int kasf_fusion(const kasf_config* cfg, const void* packed_dev, int layer, const float* att_dev,
+                const float* graph_dev, const float* bone_dev, float* out_dev, int B, void* stream);
+
+/* Final LayerNorm -> Linear(128,512) -> tanh -> Linear(512,3) (model/KASportsFormer.py:339-345). */
+int kasf_head(const kasf_config* cfg, const void* packed_dev, const float* X_dev, float* y_dev,
+              float* rep_dev, int B, void* stream);
+
+/* ---- evaluation epilogue ---------------------------------------------------------------------
+ * Replaces the per-clip numpy loop of train_and_evaluate_sp.py:55-103 and utils/error_calc.py:5-48.
+ *   pred_dev     float32 [B,T,17,3] model output (normalised); joint 0 is treated as zero (:55)
+ *   pred_flip_dev float32 [B,T,17,3] or NULL: output for the left/right flipped input; when given
+ *                the two are un-flipped and averaged first (:46-51, utils/utilities.py:128-135)
+ *   gt_dev       float32 [B,T,17,3] ground truth in mm
+ *   res_dev      float32 [B,2] (res_w,res_h);  factor_dev float32 [B,T];  action_dev int32 [B]
+ *   sums_dev     float64 [n_actions, KASF_METRIC_COLS]: ACCUMULATED (atomicAdd) per-action sums:
+ *                col 0 sum MPJPE(frames), 1 sum P-MPJPE, 2 sum accel-error, 3 #frames, 4 #accel
+ *                frames, 5..21 sum per-joint error.  Caller zeroes it and reduces across ranks.
+ *   per_frame_dev float64 [B,T,3] or NULL: per-frame (mpjpe, p_mpjpe, accel) for tests.        */
+#define KASF_METRIC_COLS 22
+int kasf_metrics(int T, const float* pred_dev, const float* pred_flip_dev, const float* gt_dev,
+                 const float* res_dev, const float* factor_dev, const int32_t* action_dev,
+                 int n_actions, double* sums_dev, double* per_frame_dev, int B, void* stream);
+
+/* Left/right flip of a clip batch (utils/utilities.py:128-135): x -> -x, swap joint pairs. */
+int kasf_joint_flip(const float* in_dev, float* out_dev, int64_t n_frames_total, void* stream);
+
+/* ---- constant tables baked into the kernels (for cross-checking host copies) ---------------
+ * which: 0 bone child[16], 1 bone parent[16], 2 limb group sizes[17], 3 limb members[17*4]
+ * (-1 padded), 4 skeleton adjacency[17*17], 5 flip permutation[17].  Returns count written. */
+int kasf_table(int which, int32_t* out, int cap);
+
+/* ---- test hook: plain tcgen05 GEMM  D[M,N] = A[M,128] * W[N,128]^T (bf16 in, fp32 out) ------- */
+int kasf_test_gemm(const float* a_dev, const float* w_dev, float* d_dev, int M, int N,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KASF_H_ */

@@ -1,0 +1,285 @@
+"""ctypes binding of libkasf.so (declared in include/kasf.h).
+
+PyTorch is used for device memory and streams only: every call passes raw device pointers and the
+current CUDA stream through the C-ABI.  There is no fallback: if the shared library is missing or
+the device is not sm_100, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Dict, Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkasf.so")
+
+KIND = {"attention": 0, "graph": 1, "bone": 2}
+MODE = {"spatial": 0, "temporal": 1}
+METRIC_COLS = 22
+
+
+class KasfConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_layers", "n_frames", "dim_feat", "dim_rep", "num_heads",
+                                          "mlp_ratio", "num_joints", "neighbour_num")]
+
+
+class KasfError(RuntimeError):
+    pass
+
+
+_lib = None
+_lock = threading.Lock()
+
+_SIGNATURES = {
+    "kasf_version": (C.c_int, []),
+    "kasf_strerror": (C.c_char_p, [C.c_int]),
+    "kasf_device_supported": (C.c_int, []),
+    "kasf_weight_entries": (C.c_int, [C.POINTER(KasfConfig)]),
+    "kasf_weight_entry": (C.c_int, [C.POINTER(KasfConfig), C.c_int, C.c_char_p, C.c_size_t,
+                                    C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "kasf_weight_image_floats": (C.c_size_t, [C.POINTER(KasfConfig)]),
+    "kasf_packed_bytes": (C.c_size_t, [C.POINTER(KasfConfig)]),
+    "kasf_pack_weights": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_void_p, C.c_size_t,
+                                    C.c_void_p]),
+    "kasf_workspace_bytes": (C.c_size_t, [C.POINTER(KasfConfig), C.c_int]),
+    "kasf_forward": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kasf_forward_launches": (C.c_int, [C.POINTER(KasfConfig), C.c_int]),
+    "kasf_kinematic_features": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                          C.c_void_p]),
+    "kasf_former_module": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "kasf_fusion": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                              C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "kasf_head": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                            C.c_int, C.c_void_p]),
+    "kasf_metrics": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "kasf_joint_flip": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "kasf_table": (C.c_int, [C.c_int, C.POINTER(C.c_int32), C.c_int]),
+    "kasf_test_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+}
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    """Load libkasf.so (once). Raises if it has not been built -- there is no fallback."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise KasfError(f"{LIB_PATH} not found: build it with `python -m "
+                                    "kasportsformer_b200.build` (nvcc, sm_100a). No CPU fallback exists.")
+                l = C.CDLL(LIB_PATH)
+                for name, (res, args) in _SIGNATURES.items():
+                    fn = getattr(l, name)
+                    fn.restype, fn.argtypes = res, args
+                _lib = l
+    return _lib
+
+
+def _check(code: int, what: str):
+    if code != 0:
+        msg = lib().kasf_strerror(code)
+        raise KasfError(f"{what} failed: {msg.decode() if msg else code} ({code})")
+
+
+def check_config_supported(cfg: dict):
+    """Host-side mirror of the C validation (include/kasf.h, kasf_config)."""
+    fixed = dict(dim_feat=128, dim_rep=512, num_heads=8, mlp_ratio=4, num_joints=17, neighbour_num=4)
+    bad = [f"{k}={cfg[k]} (built for {v})" for k, v in fixed.items() if cfg[k] != v]
+    if not (1 <= cfg["n_layers"] <= 1024):
+        bad.append(f"n_layers={cfg['n_layers']}")
+    if not (4 <= cfg["n_frames"] <= 243):
+        bad.append(f"n_frames={cfg['n_frames']} (supported: 4..243)")
+    if bad:
+        raise NotImplementedError("kasportsformer_b200 kernels are specialised; unsupported: " + ", ".join(bad))
+
+
+def c_config(cfg: dict) -> KasfConfig:
+    return KasfConfig(**{k: int(cfg[k]) for k, _ in KasfConfig._fields_})
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _require_device(dev: torch.device):
+    if dev.type != "cuda":
+        raise KasfError("kasportsformer_b200 has no CPU path")
+    with torch.cuda.device(dev):
+        _check(lib().kasf_device_supported(), "kasf_device_supported")
+
+
+# --- weights -----------------------------------------------------------------------------------
+def weight_entries(cfg: dict):
+    """[(name, offset_floats, numel)] of the canonical fp32 weight image (defined by the library)."""
+    l, cc = lib(), c_config(cfg)
+    n = l.kasf_weight_entries(C.byref(cc))
+    if n < 0:
+        _check(n, "kasf_weight_entries")
+    out, buf = [], C.create_string_buffer(256)
+    off, num = C.c_size_t(), C.c_size_t()
+    for i in range(n):
+        _check(l.kasf_weight_entry(C.byref(cc), i, buf, 256, C.byref(off), C.byref(num)), "kasf_weight_entry")
+        out.append((buf.value.decode(), off.value, num.value))
+    return out
+
+
+def build_weight_image(cfg: dict, state: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """Flatten a reference-named state dict into the canonical fp32 image (host tensor)."""
+    entries = weight_entries(cfg)
+    total = lib().kasf_weight_image_floats(C.byref(c_config(cfg)))
+    img = torch.empty(total, dtype=torch.float32)
+    names = set()
+    for name, off, numel in entries:
+        t = state[name]
+        if t.numel() != numel:
+            raise KasfError(f"{name}: expected {numel} elements, got {tuple(t.shape)}")
+        img[off:off + numel] = t.detach().reshape(-1).to(dtype=torch.float32, device="cpu")
+        names.add(name)
+    extra = [k for k in state if k not in names and state[k].is_floating_point()]
+    if extra:
+        raise KasfError(f"state has tensors the library does not know: {extra[:5]}")
+    return img
+
+
+def pack_state(cfg: dict, state: Dict[str, torch.Tensor], device: torch.device) -> torch.Tensor:
+    _require_device(device)
+    l, cc = lib(), c_config(cfg)
+    # assemble on the device the tensors live on if they already are there (no host round trip)
+    img = build_weight_image(cfg, state).to(device)
+    nbytes = l.kasf_packed_bytes(C.byref(cc))
+    blob = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        _check(l.kasf_pack_weights(C.byref(cc), _ptr(img), _ptr(blob), nbytes, _stream()), "kasf_pack_weights")
+        torch.cuda.current_stream().synchronize()   # img may be freed after return
+    return blob
+
+
+# --- forward + stages ----------------------------------------------------------------------------
+_ws_cache: Dict[tuple, torch.Tensor] = {}
+
+
+def _workspace(cfg: dict, B: int, device: torch.device) -> torch.Tensor:
+    n = lib().kasf_workspace_bytes(C.byref(c_config(cfg)), B)
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < n:
+        ws = torch.empty(n, dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def forward(cfg: dict, blob: torch.Tensor, x: torch.Tensor, return_rep: bool = False) -> torch.Tensor:
+    _require_device(x.device)
+    B, T = x.shape[0], x.shape[1]
+    y = torch.empty(B, T, 17, 3, dtype=torch.float32, device=x.device)
+    rep = torch.empty(B, T, 17, cfg["dim_rep"], dtype=torch.float32, device=x.device) if return_rep else None
+    if B == 0:
+        return rep if return_rep else y
+    with torch.cuda.device(x.device):
+        ws = _workspace(cfg, B, x.device)
+        _check(lib().kasf_forward(C.byref(c_config(cfg)), _ptr(blob), _ptr(x), _ptr(y), _ptr(rep), B,
+                                  _ptr(ws), ws.numel(), _stream()), "kasf_forward")
+    return rep if return_rep else y
+
+
+def forward_launches(cfg: dict, B: int) -> int:
+    return lib().kasf_forward_launches(C.byref(c_config(cfg)), B)
+
+
+def kinematic_features(cfg, blob, x, want_raw=True):
+    _require_device(x.device)
+    B, T = x.shape[:2]
+    f = lambda c: torch.empty(B, T, 17, c, dtype=torch.float32, device=x.device)
+    bone, limb = (f(3), f(3)) if want_raw else (None, None)
+    X, XB, XL = f(128), f(128), f(128)
+    with torch.cuda.device(x.device):
+        _check(lib().kasf_kinematic_features(C.byref(c_config(cfg)), _ptr(blob), _ptr(x), _ptr(bone),
+                                             _ptr(limb), _ptr(X), _ptr(XB), _ptr(XL), B, _stream()),
+               "kasf_kinematic_features")
+    return bone, limb, X, XB, XL
+
+
+def former_module(cfg, blob, layer, kind, mode, v, XL=None, out=None):
+    _require_device(v.device)
+    B = v.shape[0]
+    out = torch.empty_like(v) if out is None else out
+    with torch.cuda.device(v.device):
+        _check(lib().kasf_former_module(C.byref(c_config(cfg)), _ptr(blob), layer, KIND[kind], MODE[mode],
+                                        _ptr(v), _ptr(XL), _ptr(out), B, _stream()), "kasf_former_module")
+    return out
+
+
+def fusion(cfg, blob, layer, a, g, b):
+    _require_device(a.device)
+    out = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        _check(lib().kasf_fusion(C.byref(c_config(cfg)), _ptr(blob), layer, _ptr(a), _ptr(g), _ptr(b),
+                                 _ptr(out), a.shape[0], _stream()), "kasf_fusion")
+    return out
+
+
+def head(cfg, blob, X, return_rep=False):
+    _require_device(X.device)
+    B, T = X.shape[:2]
+    y = torch.empty(B, T, 17, 3, dtype=torch.float32, device=X.device)
+    rep = torch.empty(B, T, 17, 512, dtype=torch.float32, device=X.device) if return_rep else None
+    with torch.cuda.device(X.device):
+        _check(lib().kasf_head(C.byref(c_config(cfg)), _ptr(blob), _ptr(X), _ptr(y), _ptr(rep), B, _stream()),
+               "kasf_head")
+    return (y, rep) if return_rep else y
+
+
+def joint_flip(x: torch.Tensor) -> torch.Tensor:
+    _require_device(x.device)
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    frames = x.numel() // 51
+    with torch.cuda.device(x.device):
+        _check(lib().kasf_joint_flip(_ptr(x), _ptr(out), frames, _stream()), "kasf_joint_flip")
+    return out
+
+
+def metrics(pred, gt, res, factor, actions, n_actions, pred_flip=None, sums=None, want_per_frame=False):
+    _require_device(pred.device)
+    B, T = pred.shape[:2]
+    dev = pred.device
+    if sums is None:
+        sums = torch.zeros(n_actions, METRIC_COLS, dtype=torch.float64, device=dev)
+    per = torch.empty(B, T, 3, dtype=torch.float64, device=dev) if want_per_frame else None
+    with torch.cuda.device(dev):
+        _check(lib().kasf_metrics(T, _ptr(pred), _ptr(pred_flip), _ptr(gt), _ptr(res), _ptr(factor),
+                                  _ptr(actions), n_actions, _ptr(sums), _ptr(per), B, _stream()),
+               "kasf_metrics")
+    return (sums, per) if want_per_frame else sums
+
+
+def table(which: int):
+    buf = (C.c_int32 * 512)()
+    n = lib().kasf_table(which, buf, 512)
+    if n < 0:
+        _check(n, "kasf_table")
+    return list(buf[:n])
+
+
+def test_gemm(a: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    _require_device(a.device)
+    M, N = a.shape[0], w.shape[0]
+    d = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _check(lib().kasf_test_gemm(_ptr(a), _ptr(w), _ptr(d), M, N, _stream()), "kasf_test_gemm")
+    return d

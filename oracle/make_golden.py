@@ -1,0 +1,198 @@
+"""Record golden vectors from the UNMODIFIED reference (CPU) into tests/golden/.  Run in the build
+container only:  python -m oracle.make_golden
+
+TEST INFRASTRUCTURE.  Weights and inputs come from `kasportsformer_b200.synthetic` (bit-reproducible
+anywhere), are loaded into the real reference modules with `load_state_dict(strict=True)`, and the
+reference's own forward / numpy metric functions / eval loop produce the recorded outputs.  Stage
+tensors are captured with forward hooks on the reference submodules and stored sub-sampled
+(every 8th channel) plus float64 sums of the full tensor, to keep the fixtures small.
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_shim                                    # noqa: E402
+from kasportsformer_b200 import synthetic                      # noqa: E402
+from kasportsformer_b200.model import KASportsFormer as Ours   # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+CH_STRIDE = 8
+
+
+def cfg_of(**over):
+    c = dict(n_layers=26, n_frames=27, dim_feat=128, dim_rep=512, num_heads=8, mlp_ratio=4,
+             num_joints=17, neighbour_num=4)
+    c.update(over)
+    return c
+
+
+def sample(t: torch.Tensor) -> np.ndarray:
+    t = t.detach()
+    return (t[..., ::CH_STRIDE] if t.shape[-1] >= 64 else t).contiguous().numpy()
+
+
+def record_stages(cfg, state, x, per_module=True):
+    """Run the real reference, capturing stage outputs by hooks. Returns dict name -> tensor."""
+    m = ref_shim.build_reference(cfg, state)
+    cap = {}
+
+    def hook(name):
+        def f(mod, inp, out):
+            cap[name] = out.detach().clone()
+        return f
+    hs = [m.bone_refusion.register_forward_hook(hook("limb")),
+          m.joints_embed.register_forward_hook(hook("joints_embed_raw")),
+          m.norm.register_forward_hook(hook("final_norm"))]
+    for l, layer in enumerate(m.layers_with_bone):
+        hs.append(layer.register_forward_hook(hook(f"layers_with_bone.{l}.out")))
+        for br in ("att", "graph", "bone") if per_module else ():
+            for mode in ("spatial", "temporal"):
+                fm = getattr(layer, f"{br}_{mode}")
+                p = f"layers_with_bone.{l}.{br}_{mode}."
+                hs.append(fm.mixer.register_forward_hook(hook(p + "mixer")))
+                hs.append(fm.mlp.register_forward_hook(hook(p + "mlp")))
+                hs.append(fm.register_forward_hook(hook(p + "out")))
+    bone_decomposer, _, _ = ref_shim.reference_modules()
+    with torch.no_grad():
+        y = m(x)
+        rep = m(x, return_rep=True)
+        cap["bone"] = bone_decomposer(x)
+        # embeddings as forward computes them (model/KASportsFormer.py:325-330)
+        cap["X"] = m.joints_embed(x) + m.pos_embed
+        cap["XB"] = m.bone_embed(cap["bone"]) + m.bone_pos_embed
+        cap["XL"] = m.limb_embed(cap["limb"]) + m.limb_pos_embed
+    for h in hs:
+        h.remove()
+    cap.pop("joints_embed_raw")
+    cap["y"], cap["rep"] = y, rep
+    return cap
+
+
+def save_stage_fixture(fname, cfg, seed, regime, B, clip_seed, kind, per_module=True):
+    state = synthetic.make_state(cfg, seed, regime)
+    x = synthetic.make_clips(B, cfg["n_frames"], clip_seed, kind)
+    cap = record_stages(cfg, state, x, per_module)
+    out = {"meta": json.dumps(dict(cfg=cfg, seed=seed, regime=regime, B=B, clip_seed=clip_seed, kind=kind,
+                                   ch_stride=CH_STRIDE, state_digest=synthetic.state_digest(state),
+                                   x_sha=hashlib.sha256(x.numpy().tobytes()).hexdigest(),
+                                   torch=torch.__version__))}
+    for k, v in cap.items():
+        out["t:" + k] = sample(v)
+        out["s:" + k] = np.array([v.double().sum().item(), v.double().abs().sum().item()])
+    np.savez_compressed(os.path.join(OUT, fname), **out)
+    print(fname, len(cap), "tensors;", "y mean|.|", cap["y"].abs().mean().item())
+
+
+def save_metrics_fixture():
+    _, ec, joint_flip = ref_shim.reference_modules()
+    B, T = 6, 27
+    g = np.random.Generator(np.random.PCG64(3))
+    pred = (g.random((B, T, 17, 3)) - 0.5).astype(np.float32)
+    pred_flip = (g.random((B, T, 17, 3)) - 0.5).astype(np.float32)
+    gt, factor, res, _ = synthetic.make_labels(B, T, seed=5, n_actions=1)
+    res[3:] = torch.tensor([1216.0, 1936.0])
+    actions = ["a", "b", "a", "c", "b", "a"]
+    out = dict(pred=pred, pred_flip=pred_flip, gt=gt.numpy(), factor=factor.numpy(), res=res.numpy(),
+               actions=np.array([0, 1, 0, 2, 1, 0], np.int32))
+    # (1) raw metric functions on mm-scale data (reference utils/error_calc.py)
+    pm = (g.random((T, 17, 3)) * 500).astype(np.float64)
+    tm = (g.random((T, 17, 3)) * 500).astype(np.float64)
+    out.update(raw_pred=pm, raw_gt=tm, raw_mpjpe=ec.mpjpe_calc(pm, tm), raw_jpe=ec.jpe_calc(pm, tm),
+               raw_acc=ec.acc_error_calc(pm, tm), raw_pmpjpe=ec.p_mpjpe_calc(pm.copy(), tm.copy()))
+    # (2) joint_flip
+    out["flip_of_pred"] = joint_flip(torch.from_numpy(pred)).numpy()
+    # (3) the whole eval loop of train_and_evaluate_sp.py:27-149, unmodified, fed by a fake model
+    ev, ED = ref_shim.reference_eval_loop()
+
+    class Fake(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.calls = 0
+
+        def forward(self, x):
+            self.calls += 1
+            return torch.from_numpy(pred if self.calls % 2 == 1 else pred_flip).clone()
+
+    class Log:
+        def info(self, *_):
+            pass
+    for flip in (False, True):
+        fake = Fake()
+        loader = [(torch.zeros(B, T, 17, 3), gt, factor, actions, res)]
+        args = ED(num_joints=17, flip=flip, eval_only=True)
+        r = ev(args, fake, loader, "cpu", 0, Log())
+        tag = "flip" if flip else "noflip"
+        out[f"eval_{tag}"] = np.array([r["mpjpe"], r["p_mpjpe"], r["acceleration_error"]])
+        out[f"eval_{tag}_joint"] = np.asarray(r["mpjpe_joint"])
+        out[f"eval_{tag}_names"] = np.array(r["activity_name_sequence"])
+        out[f"eval_{tag}_per_action"] = np.asarray(r["mpjpe_activity"])
+    np.savez_compressed(os.path.join(OUT, "metrics.npz"), **out)
+    print("metrics.npz", out["eval_noflip"], out["eval_flip"])
+
+
+def save_refinit_fixture():
+    """Reference constructed under torch.manual_seed(114514) (configs/*.yaml:17) -- the known-answer
+    recipe of SURVEY.md section 8c -- and proof that our holder tree draws the same initial weights."""
+    cfg = cfg_of()
+    torch.manual_seed(114514)
+    m = ref_shim.build_reference(cfg)
+    torch.manual_seed(114514)
+    ours = Ours(num_heads=8)
+    rs, os_ = m.state_dict(), ours.state_dict()
+    assert list(rs.keys()) == list(os_.keys()), "state_dict key order differs"
+    assert all(torch.equal(rs[k], os_[k]) for k in rs), "initial weights differ"
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(16, 27, 17, 3, generator=g) * 0.5
+    x[..., 2] = 1.0
+    gt = (torch.randn(16, 27, 17, 3, generator=g) * 250)
+    factor = 2 + 3 * torch.rand(16, 27, generator=g)
+    with torch.no_grad():
+        y = m(x)
+    _, ec, _ = ref_shim.reference_modules()
+    # eval protocol without flip (train_and_evaluate_sp.py:55-81), reference functions
+    p = y.clone().numpy().astype(np.float64)
+    p[:, :, 0, :] = 0
+    mp, pmp = [], []
+    for i in range(16):
+        d = p[i].copy()
+        d[:, :, :2] = (d[:, :, :2] + np.array([1, 1216 / 1312])) * 1312 / 2
+        d[:, :, 2:] = d[:, :, 2:] * 1312 / 2
+        d *= factor[i].numpy().astype(np.float64)[:, None, None]
+        d = d - d[:, 0:1]
+        t = gt[i].numpy().astype(np.float64)
+        t = t - t[:, 0:1]
+        mp.extend(ec.mpjpe_calc(d, t))
+        pmp.extend(ec.p_mpjpe_calc(d, t))
+    np.savez_compressed(os.path.join(OUT, "kat_refinit.npz"), x=x.numpy(), y=y.numpy(), gt=gt.numpy(),
+                        factor=factor.numpy(), mpjpe=np.mean(mp), p_mpjpe=np.mean(pmp),
+                        init_digest=synthetic.state_digest({k: v for k, v in rs.items()}),
+                        n_keys=len(rs), n_params=sum(p.numel() for p in m.parameters()))
+    print("kat_refinit: y[0,0,1]=", y[0, 0, 1].tolist(), "sum", y.double().sum().item(),
+          "MPJPE", np.mean(mp), "P-MPJPE", np.mean(pmp), "keys", len(rs))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    save_refinit_fixture()
+    save_metrics_fixture()
+    # acceptance regime: default init, full depth
+    save_stage_fixture("full_default_T27.npz", cfg_of(), seed=0, regime="default", B=1, clip_seed=0, kind="det",
+                       per_module=False)
+    # stage parity regime: trained-like magnitudes
+    save_stage_fixture("stress_L2_T27.npz", cfg_of(n_layers=2), seed=1, regime="stress", B=1, clip_seed=1, kind="det")
+    save_stage_fixture("stress_L1_T81.npz", cfg_of(n_layers=1, n_frames=81), seed=2, regime="stress", B=1,
+                       clip_seed=2, kind="gt")
+    save_stage_fixture("stress_L1_T9.npz", cfg_of(n_layers=1, n_frames=9), seed=3, regime="stress", B=2,
+                       clip_seed=3, kind="det")
+
+
+if __name__ == "__main__":
+    main()
