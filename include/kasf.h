@@ -145,6 +145,9 @@ int kasf_table(int which, int32_t* out, int cap);
 int kasf_test_gemm(const float* a_dev, const float* w_dev, float* d_dev, int M, int N,
                    void* stream);
 
+/* ---- self-test hook: the metric kernel's Procrustes routine (same source) executed on the host. */
+double kasf_selftest_p_mpjpe_host(const double* pred_17x3, const double* gt_17x3);
+
 #ifdef __cplusplus
 }
 #endif

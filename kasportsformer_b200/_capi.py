@@ -62,6 +62,7 @@ _SIGNATURES = {
     "kasf_joint_flip": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "kasf_table": (C.c_int, [C.c_int, C.POINTER(C.c_int32), C.c_int]),
     "kasf_test_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "kasf_selftest_p_mpjpe_host": (C.c_double, [C.c_void_p, C.c_void_p]),
 }
 
 

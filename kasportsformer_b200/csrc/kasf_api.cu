@@ -1,0 +1,244 @@
+// kasf_api.cu -- extern "C" entry points of libkasf.so (declared in include/kasf.h) and the
+// orchestration of the forward pass (reference model/KASportsFormer.py:320-347).
+#include "kasf_internal.h"
+
+using namespace kasf;
+
+namespace {
+
+int device_ok() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return KASF_EARCH;
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return KASF_EARCH;
+    return major == 10 ? KASF_OK : KASF_EARCH;
+}
+
+// clips processed per pass of kasf_forward: bounds the workspace (6 fp32 streams of [chunk*T*17,128]).
+int clip_chunk(const kasf_config* cfg, int B) {
+    const long long per_clip = (long long)cfg->n_frames * J * D * 4 * 6;
+    long long c = (3LL << 30) / per_clip;   // ~3 GiB of streams
+    if (c < 1) c = 1;
+    return (int)(c < B ? c : B);
+}
+
+struct Streams {
+    float *X, *XB, *XL, *A, *G, *Bn;
+};
+Streams carve(void* ws, long long tokens) {
+    const size_t n = ((size_t)tokens * D * 4 + 1023) / 1024 * 1024;
+    uint8_t* p = static_cast<uint8_t*>(ws);
+    Streams s;
+    s.X = (float*)(p), s.XB = (float*)(p + n), s.XL = (float*)(p + 2 * n);
+    s.A = (float*)(p + 3 * n), s.G = (float*)(p + 4 * n), s.Bn = (float*)(p + 5 * n);
+    return s;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kasf_version(void) { return KASF_VERSION; }
+
+const char* kasf_strerror(int code) {
+    switch (code) {
+        case KASF_OK: return "ok";
+        case KASF_EINVAL: return "invalid argument";
+        case KASF_ESHAPE: return "shape/config not implemented by this build";
+        case KASF_EARCH: return "device is not sm_100 (no fallback path exists)";
+        case KASF_ENOMEM: return "caller-provided buffer too small";
+        default:
+            if (code <= -1000) return cudaGetErrorString((cudaError_t)(-code - 1000));
+            return "unknown error";
+    }
+}
+
+int kasf_device_supported(void) { return device_ok(); }
+
+int kasf_weight_entries(const kasf_config* cfg) {
+    int rc = config_ok(cfg);
+    if (rc) return rc;
+    int n = 0;
+    walk_image(cfg, nullptr, nullptr, [&](const char*, size_t, size_t) { ++n; });
+    return n;
+}
+
+int kasf_weight_entry(const kasf_config* cfg, int index, char* name, size_t name_cap, size_t* offset_floats,
+                      size_t* numel) {
+    int rc = config_ok(cfg);
+    if (rc) return rc;
+    if (!name || !offset_floats || !numel || index < 0) return KASF_EINVAL;
+    int n = 0;
+    bool found = false;
+    walk_image(cfg, nullptr, nullptr, [&](const char* nm, size_t off, size_t cnt) {
+        if (n++ == index) {
+            found = true;
+            snprintf(name, name_cap, "%s", nm);
+            *offset_floats = off;
+            *numel = cnt;
+        }
+    });
+    return found ? KASF_OK : KASF_EINVAL;
+}
+
+size_t kasf_weight_image_floats(const kasf_config* cfg) {
+    if (config_ok(cfg)) return 0;
+    return walk_image(cfg, nullptr, nullptr, [](const char*, size_t, size_t) {});
+}
+
+size_t kasf_packed_bytes(const kasf_config* cfg) { return config_ok(cfg) ? 0 : packed_bytes(cfg); }
+
+int kasf_pack_weights(const kasf_config* cfg, const float* image_dev, void* packed_dev, size_t packed_cap,
+                      void* stream) {
+    int rc = config_ok(cfg);
+    if (rc) return rc;
+    if (!image_dev || !packed_dev) return KASF_EINVAL;
+    if ((rc = device_ok())) return rc;
+    return pack_weights(cfg, image_dev, packed_dev, packed_cap, (cudaStream_t)stream);
+}
+
+size_t kasf_workspace_bytes(const kasf_config* cfg, int B) {
+    if (config_ok(cfg) || B <= 0) return 0;
+    const long long tokens = (long long)clip_chunk(cfg, B) * cfg->n_frames * J;
+    return 6 * (((size_t)tokens * D * 4 + 1023) / 1024 * 1024);
+}
+
+int kasf_forward_launches(const kasf_config* cfg, int B) {
+    if (config_ok(cfg) || B <= 0) return 0;
+    const int chunk = clip_chunk(cfg, B);
+    const int passes = (B + chunk - 1) / chunk;
+    return passes * (1 + cfg->n_layers * 7 + 1);
+}
+
+int kasf_kinematic_features(const kasf_config* cfg, const void* packed_dev, const float* x_dev, float* bone_dev,
+                            float* limb_dev, float* X_dev, float* XB_dev, float* XL_dev, int B, void* stream) {
+    int rc = config_ok(cfg);
+    if (rc) return rc;
+    if (!packed_dev || !x_dev || !X_dev || !XB_dev || !XL_dev || B < 0) return KASF_EINVAL;
+    if ((rc = device_ok())) return rc;
+    return launch_features((const uint8_t*)packed_dev, x_dev, bone_dev, limb_dev, X_dev, XB_dev, XL_dev,
+                           (long long)B * cfg->n_frames, (cudaStream_t)stream);
+}
+
+int kasf_former_module(const kasf_config* cfg, const void* packed_dev, int layer, int kind, int mode,
+                       const float* in_dev, const float* XL_dev, float* out_dev, int B, void* stream) {
+    int rc = config_ok(cfg);
+    if (rc) return rc;
+    if (!packed_dev || !in_dev || !out_dev || B < 0 || layer < 0 || layer >= cfg->n_layers) return KASF_EINVAL;
+    if ((rc = device_ok())) return rc;
+    return launch_former_module((const uint8_t*)packed_dev, layer, kind, mode, in_dev, XL_dev, out_dev, B,
+                                cfg->n_frames, (cudaStream_t)stream);
+}
+
+int kasf_fusion(const kasf_config* cfg, const void* packed_dev, int layer, const float* att_dev,
+                const float* graph_dev, const float* bone_dev, float* out_dev, int B, void* stream) {
+    int rc = config_ok(cfg);
+    if (rc) return rc;
+    if (!packed_dev || !att_dev || !graph_dev || !bone_dev || !out_dev || B < 0 || layer < 0 || layer >= cfg->n_layers)
+        return KASF_EINVAL;
+    if ((rc = device_ok())) return rc;
+    return launch_fusion((const uint8_t*)packed_dev, layer, att_dev, graph_dev, bone_dev, out_dev,
+                         (long long)B * cfg->n_frames * J, (cudaStream_t)stream);
+}
+
+int kasf_head(const kasf_config* cfg, const void* packed_dev, const float* X_dev, float* y_dev, float* rep_dev,
+              int B, void* stream) {
+    int rc = config_ok(cfg);
+    if (rc) return rc;
+    if (!packed_dev || !X_dev || (!y_dev && !rep_dev) || B < 0) return KASF_EINVAL;
+    if ((rc = device_ok())) return rc;
+    return launch_head((const uint8_t*)packed_dev, X_dev, y_dev, rep_dev, (long long)B * cfg->n_frames * J,
+                       (cudaStream_t)stream);
+}
+
+int kasf_forward(const kasf_config* cfg, const void* packed_dev, const float* x_dev, float* y_dev, float* rep_dev,
+                 int B, void* ws_dev, size_t ws_bytes, void* stream) {
+    int rc = config_ok(cfg);
+    if (rc) return rc;
+    if (!packed_dev || !x_dev || (!y_dev && !rep_dev) || !ws_dev || B < 0) return KASF_EINVAL;
+    if (((uintptr_t)ws_dev & 255) != 0) return KASF_EINVAL;
+    if (ws_bytes < kasf_workspace_bytes(cfg, B)) return KASF_ENOMEM;
+    if ((rc = device_ok())) return rc;
+    const uint8_t* blob = (const uint8_t*)packed_dev;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int T = cfg->n_frames;
+    const int chunk = clip_chunk(cfg, B);
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int nb = B - b0 < chunk ? B - b0 : chunk;
+        const long long tokens = (long long)nb * T * J;
+        Streams s = carve(ws_dev, (long long)chunk * T * J);
+        const float* x = x_dev + (size_t)b0 * T * J * 3;
+        if ((rc = launch_features(blob, x, nullptr, nullptr, s.X, s.XB, s.XL, (long long)nb * T, st))) return rc;
+        for (int l = 0; l < cfg->n_layers; ++l) {
+            // three branches, each spatial module then temporal module (KASportsFormer.py:268-275)
+            const float* bone_src = l == 0 ? s.XB : s.X;
+            if ((rc = launch_former_module(blob, l, KASF_KIND_ATTENTION, KASF_MODE_SPATIAL, s.X, nullptr, s.A, nb, T, st))) return rc;
+            if ((rc = launch_former_module(blob, l, KASF_KIND_ATTENTION, KASF_MODE_TEMPORAL, s.A, nullptr, s.A, nb, T, st))) return rc;
+            if ((rc = launch_former_module(blob, l, KASF_KIND_GRAPH, KASF_MODE_SPATIAL, s.X, nullptr, s.G, nb, T, st))) return rc;
+            if ((rc = launch_former_module(blob, l, KASF_KIND_GRAPH, KASF_MODE_TEMPORAL, s.G, nullptr, s.G, nb, T, st))) return rc;
+            if ((rc = launch_former_module(blob, l, KASF_KIND_BONE, KASF_MODE_SPATIAL, bone_src, s.XL, s.Bn, nb, T, st))) return rc;
+            if ((rc = launch_former_module(blob, l, KASF_KIND_BONE, KASF_MODE_TEMPORAL, s.Bn, s.XL, s.Bn, nb, T, st))) return rc;
+            if ((rc = launch_fusion(blob, l, s.A, s.G, s.Bn, s.X, tokens, st))) return rc;
+        }
+        float* y = y_dev ? y_dev + (size_t)b0 * T * J * 3 : nullptr;
+        float* rep = rep_dev ? rep_dev + (size_t)b0 * T * J * REP : nullptr;
+        if ((rc = launch_head(blob, s.X, y, rep, tokens, st))) return rc;
+    }
+    return KASF_OK;
+}
+
+int kasf_metrics(int T, const float* pred_dev, const float* pred_flip_dev, const float* gt_dev, const float* res_dev,
+                 const float* factor_dev, const int32_t* action_dev, int n_actions, double* sums_dev,
+                 double* per_frame_dev, int B, void* stream) {
+    if (!pred_dev || !gt_dev || !res_dev || !factor_dev || !sums_dev || B < 0) return KASF_EINVAL;
+    int rc = device_ok();
+    if (rc) return rc;
+    return launch_metrics(T, pred_dev, pred_flip_dev, gt_dev, res_dev, factor_dev, action_dev, n_actions, sums_dev,
+                          per_frame_dev, B, (cudaStream_t)stream);
+}
+
+int kasf_joint_flip(const float* in_dev, float* out_dev, int64_t n_frames_total, void* stream) {
+    if (!in_dev || !out_dev || n_frames_total < 0) return KASF_EINVAL;
+    int rc = device_ok();
+    if (rc) return rc;
+    return launch_flip(in_dev, out_dev, n_frames_total, (cudaStream_t)stream);
+}
+
+int kasf_table(int which, int32_t* out, int cap) {
+    if (!out) return KASF_EINVAL;
+    const int* src = nullptr;
+    int n = 0;
+    int adj[289];
+    switch (which) {
+        case 0: src = h_bone_child, n = 16; break;
+        case 1: src = h_bone_parent, n = 16; break;
+        case 2: src = h_limb_size, n = 17; break;
+        case 3: src = h_limb_member, n = 68; break;
+        case 4:
+            for (int i = 0; i < 289; ++i) adj[i] = 0;
+            for (int i = 0; i < 17; ++i)
+                for (int k = 0; k < 4; ++k)
+                    if (h_nbr[i * 4 + k] >= 0) adj[i * 17 + h_nbr[i * 4 + k]] = 1;
+            src = adj, n = 289;
+            break;
+        case 5: src = h_flip, n = 17; break;
+        default: return KASF_EINVAL;
+    }
+    if (cap < n) return KASF_ENOMEM;
+    for (int i = 0; i < n; ++i) out[i] = src[i];
+    return n;
+}
+
+int kasf_test_gemm(const float* a_dev, const float* w_dev, float* d_dev, int M, int N, void* stream) {
+    if (!a_dev || !w_dev || !d_dev) return KASF_EINVAL;
+    int rc = device_ok();
+    if (rc) return rc;
+    return launch_test_gemm(a_dev, w_dev, d_dev, M, N, (cudaStream_t)stream);
+}
+
+// self-test hook: the Procrustes routine of the metric kernel executed on the host (same source)
+double kasf_selftest_p_mpjpe_host(const double* pred_17x3, const double* gt_17x3) {
+    return host_p_mpjpe(pred_17x3, gt_17x3);
+}
+
+}  // extern "C"

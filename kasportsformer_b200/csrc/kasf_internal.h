@@ -1,0 +1,34 @@
+// kasf_internal.h -- declarations shared between the translation units of libkasf.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kasf_layout.h"
+#include "kasf_ptx.cuh"
+#include "kasf_tables.cuh"
+
+namespace kasf {
+
+// CUDA launch status -> C-ABI code
+inline int cuda_status() {
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? KASF_OK : -(1000 + (int)e);
+}
+
+int pack_weights(const kasf_config* cfg, const float* image, void* packed, size_t cap, cudaStream_t st);
+
+int launch_features(const uint8_t* blob, const float* x, float* bone, float* limb, float* X, float* XB, float* XL,
+                    long long frames, cudaStream_t st);
+int launch_head(const uint8_t* blob, const float* X, float* y, float* rep, long long tokens, cudaStream_t st);
+int launch_fusion(const uint8_t* blob, int layer, const float* a, const float* g, const float* b, float* out,
+                  long long tokens, cudaStream_t st);
+int launch_former_module(const uint8_t* blob, int layer, int kind, int mode, const float* in, const float* XL,
+                         float* out, int B, int T, cudaStream_t st);
+int launch_metrics(int T, const float* pred, const float* pred_flip, const float* gt, const float* res,
+                   const float* factor, const int32_t* action, int n_actions, double* sums, double* per_frame,
+                   int B, cudaStream_t st);
+double host_p_mpjpe(const double* p, const double* g);
+int launch_flip(const float* in, float* out, long long frames, cudaStream_t st);
+int launch_test_gemm(const float* a, const float* w, float* d, int M, int N, cudaStream_t st);
+
+}  // namespace kasf

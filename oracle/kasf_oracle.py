@@ -71,8 +71,21 @@ def gelu_erf(v: Tensor) -> Tensor:
     return F.gelu(v)
 
 
-def linear(v: Tensor, w: Tensor, b: Optional[Tensor] = None) -> Tensor:
+# When True, the dense projections of the FormerModules round their operands to bfloat16 (fp32
+# accumulation) at the points where the CUDA kernels do (tensor-core operands; K/V tiles), so the
+# kernels can be compared with a tight tolerance.  Embeddings, head, LayerNorm, softmax, similarity
+# stay fp32 in the kernels and here.  Default False = the reference's fp32 arithmetic.
+EMULATE_BF16 = False
+
+
+def _q(t: Tensor) -> Tensor:
+    return t.to(torch.bfloat16).to(t.dtype) if EMULATE_BF16 else t
+
+
+def linear(v: Tensor, w: Tensor, b: Optional[Tensor] = None, exact: bool = False) -> Tensor:
     """y = v W^T + b  (torch nn.Linear convention; W is [out, in])."""
+    if EMULATE_BF16 and not exact:
+        return F.linear(_q(v), _q(w), b)
     return F.linear(v, w, b)
 
 
@@ -86,17 +99,17 @@ def limb_features(state: State, x: Tensor) -> Tensor:
         for c, nm in enumerate(LIMB_CH):
             pre = f"bone_refusion.mlp_layers.{g}.{nm}."
             v = x[:, :, idx, c]                                         # [B,T,n]
-            h = gelu_erf(linear(v, state[pre + "fc1.weight"], state[pre + "fc1.bias"]))
-            chans.append(linear(h, state[pre + "fc2.weight"], state[pre + "fc2.bias"]))  # [B,T,1]
+            h = gelu_erf(linear(v, state[pre + "fc1.weight"], state[pre + "fc1.bias"], exact=True))
+            chans.append(linear(h, state[pre + "fc2.weight"], state[pre + "fc2.bias"], exact=True))  # [B,T,1]
         outs.append(torch.cat(chans, dim=-1).unsqueeze(-2))             # [B,T,1,3]
     return torch.cat(outs, dim=-2)
 
 
 def embed(state: State, x: Tensor, bone: Tensor, limb: Tensor):
     """reference model/KASportsFormer.py:325-330."""
-    X = linear(x, state["joints_embed.weight"], state["joints_embed.bias"]) + state["pos_embed"]
-    XB = linear(bone, state["bone_embed.weight"], state["bone_embed.bias"]) + state["bone_pos_embed"]
-    XL = linear(limb, state["limb_embed.weight"], state["limb_embed.bias"]) + state["limb_pos_embed"]
+    X = linear(x, state["joints_embed.weight"], state["joints_embed.bias"], exact=True) + state["pos_embed"]
+    XB = linear(bone, state["bone_embed.weight"], state["bone_embed.bias"], exact=True) + state["bone_pos_embed"]
+    XL = linear(limb, state["limb_embed.weight"], state["limb_embed.bias"], exact=True) + state["limb_pos_embed"]
     return X, XB, XL
 
 
@@ -113,7 +126,7 @@ def _attend(q: Tensor, k: Tensor, v: Tensor, mode: str, heads: int) -> Tensor:
     scale = d ** -0.5
     def split(t):  # [B,T,J,H,d] -> [B,H,T,J,d]
         return t.reshape(B, T, J, heads, d).permute(0, 3, 1, 2, 4)
-    q, k, v = split(q), split(k), split(v)
+    q, k, v = split(q), split(_q(k)), split(_q(v))     # K/V tiles are kept in bf16 on chip
     if mode == "temporal":
         q, k, v = q.transpose(2, 3), k.transpose(2, 3), v.transpose(2, 3)   # [B,H,J,T,d]
     att = torch.softmax((q @ k.transpose(-2, -1)) * scale, dim=-1)
@@ -220,7 +233,7 @@ def former_module(state: State, pre: str, v: Tensor, xl: Optional[Tensor], kind:
 
 def fuse(state: State, pre: str, a: Tensor, g: Tensor, b: Tensor) -> Tensor:
     """reference model/KASportsFormer.py:279-282 (adaptive fusion)."""
-    logits = linear(torch.cat([a, g, b], dim=-1), state[pre + "weight"], state[pre + "bias"])
+    logits = linear(torch.cat([a, g, b], dim=-1), state[pre + "weight"], state[pre + "bias"], exact=True)
     alpha = torch.softmax(logits, dim=-1)
     return a * alpha[..., 0:1] + g * alpha[..., 1:2] + b * alpha[..., 2:3]
 
@@ -244,10 +257,10 @@ def layer(state: State, l: int, X: Tensor, XB: Optional[Tensor], XL: Tensor, cfg
 def head(state: State, X: Tensor, return_rep: bool = False) -> Tensor:
     """reference model/KASportsFormer.py:339-345."""
     z = layer_norm(X, state["norm.weight"], state["norm.bias"])
-    rep = torch.tanh(linear(z, state["rep_logit.fc.weight"], state["rep_logit.fc.bias"]))
+    rep = torch.tanh(linear(z, state["rep_logit.fc.weight"], state["rep_logit.fc.bias"], exact=True))
     if return_rep:
         return rep
-    return linear(rep, state["head.weight"], state["head.bias"])
+    return linear(rep, state["head.weight"], state["head.bias"], exact=True)
 
 
 def forward(state: State, x: Tensor, cfg: Optional[dict] = None, return_rep: bool = False,
