@@ -91,6 +91,16 @@ int    kasf_forward(const kasf_config* cfg, const void* packed_dev, const float*
                     void* stream);
 /* Number of kernel launches one kasf_forward(B) enqueues (for bench accounting). */
 int    kasf_forward_launches(const kasf_config* cfg, int B);
+/* Same forward, additionally recording events[0] before the first launch and events[i] after the
+ * i-th launch on `stream` (n_events >= launches + 1), so a caller can read per-kernel device times
+ * of the very launches it is timing.  Launch order per pass: features, then per layer att_s, att_t,
+ * graph_s, graph_t, bone_s, bone_t, fusion, and finally head.  Events come from kasf_event_create. */
+int    kasf_forward_timed(const kasf_config* cfg, const void* packed_dev, const float* x_dev,
+                          float* y_dev, float* rep_dev, int B, void* ws_dev, size_t ws_bytes,
+                          void* stream, void** events, int n_events);
+void*  kasf_event_create(void);
+void   kasf_event_destroy(void* event);
+float  kasf_event_elapsed_ms(void* start, void* stop);   /* after the stream has been synchronised */
 
 /* ---- per-stage entry points (used by the parity tests; same kernels kasf_forward runs) -------
  * Kinematic anatomy features + the three embeddings.  Replaces bone_decomposer

@@ -48,6 +48,11 @@ _SIGNATURES = {
     "kasf_forward": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kasf_forward_launches": (C.c_int, [C.POINTER(KasfConfig), C.c_int]),
+    "kasf_forward_timed": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p), C.c_int]),
+    "kasf_event_create": (C.c_void_p, []),
+    "kasf_event_destroy": (None, [C.c_void_p]),
+    "kasf_event_elapsed_ms": (C.c_float, [C.c_void_p, C.c_void_p]),
     "kasf_kinematic_features": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                           C.c_void_p]),
@@ -196,6 +201,37 @@ def forward(cfg: dict, blob: torch.Tensor, x: torch.Tensor, return_rep: bool = F
         _check(lib().kasf_forward(C.byref(c_config(cfg)), _ptr(blob), _ptr(x), _ptr(y), _ptr(rep), B,
                                   _ptr(ws), ws.numel(), _stream()), "kasf_forward")
     return rep if return_rep else y
+
+
+class LaunchTimer:
+    """Per-launch CUDA events for `forward(..., timer=...)`: device time of every kernel of a forward."""
+
+    def __init__(self, cfg: dict, B: int):
+        self.n = lib().kasf_forward_launches(C.byref(c_config(cfg)), B) + 1
+        self.events = (C.c_void_p * self.n)(*[lib().kasf_event_create() for _ in range(self.n)])
+
+    def launch_ms(self):
+        """[ms] per launch, in launch order (call after synchronising the stream)."""
+        return [lib().kasf_event_elapsed_ms(self.events[i], self.events[i + 1]) for i in range(self.n - 1)]
+
+    def close(self):
+        for e in self.events:
+            lib().kasf_event_destroy(e)
+
+
+def forward_into(cfg: dict, blob: torch.Tensor, x: torch.Tensor, y: torch.Tensor, timer: "LaunchTimer" = None):
+    """Forward into a preallocated output (bench loop: no allocation inside the timed region)."""
+    B = x.shape[0]
+    with torch.cuda.device(x.device):
+        ws = _workspace(cfg, B, x.device)
+        if timer is None:
+            _check(lib().kasf_forward(C.byref(c_config(cfg)), _ptr(blob), _ptr(x), _ptr(y), None, B,
+                                      _ptr(ws), ws.numel(), _stream()), "kasf_forward")
+        else:
+            _check(lib().kasf_forward_timed(C.byref(c_config(cfg)), _ptr(blob), _ptr(x), _ptr(y), None, B,
+                                            _ptr(ws), ws.numel(), _stream(), timer.events, timer.n),
+                   "kasf_forward_timed")
+    return y
 
 
 def forward_launches(cfg: dict, B: int) -> int:

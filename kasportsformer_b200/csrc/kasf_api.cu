@@ -151,8 +151,8 @@ int kasf_head(const kasf_config* cfg, const void* packed_dev, const float* X_dev
                        (cudaStream_t)stream);
 }
 
-int kasf_forward(const kasf_config* cfg, const void* packed_dev, const float* x_dev, float* y_dev, float* rep_dev,
-                 int B, void* ws_dev, size_t ws_bytes, void* stream) {
+static int forward_impl(const kasf_config* cfg, const void* packed_dev, const float* x_dev, float* y_dev,
+                        float* rep_dev, int B, void* ws_dev, size_t ws_bytes, void* stream, void** events) {
     int rc = config_ok(cfg);
     if (rc) return rc;
     if (!packed_dev || !x_dev || (!y_dev && !rep_dev) || !ws_dev || B < 0) return KASF_EINVAL;
@@ -163,28 +163,66 @@ int kasf_forward(const kasf_config* cfg, const void* packed_dev, const float* x_
     cudaStream_t st = (cudaStream_t)stream;
     const int T = cfg->n_frames;
     const int chunk = clip_chunk(cfg, B);
+    int ev = 0;
+#define KASF_MARK() do { if (events) cudaEventRecord((cudaEvent_t)events[ev++], st); } while (0)
+    KASF_MARK();
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int nb = B - b0 < chunk ? B - b0 : chunk;
         const long long tokens = (long long)nb * T * J;
         Streams s = carve(ws_dev, (long long)chunk * T * J);
         const float* x = x_dev + (size_t)b0 * T * J * 3;
         if ((rc = launch_features(blob, x, nullptr, nullptr, s.X, s.XB, s.XL, (long long)nb * T, st))) return rc;
+        KASF_MARK();
         for (int l = 0; l < cfg->n_layers; ++l) {
             // three branches, each spatial module then temporal module (KASportsFormer.py:268-275)
             const float* bone_src = l == 0 ? s.XB : s.X;
             if ((rc = launch_former_module(blob, l, KASF_KIND_ATTENTION, KASF_MODE_SPATIAL, s.X, nullptr, s.A, nb, T, st))) return rc;
+            KASF_MARK();
             if ((rc = launch_former_module(blob, l, KASF_KIND_ATTENTION, KASF_MODE_TEMPORAL, s.A, nullptr, s.A, nb, T, st))) return rc;
+            KASF_MARK();
             if ((rc = launch_former_module(blob, l, KASF_KIND_GRAPH, KASF_MODE_SPATIAL, s.X, nullptr, s.G, nb, T, st))) return rc;
+            KASF_MARK();
             if ((rc = launch_former_module(blob, l, KASF_KIND_GRAPH, KASF_MODE_TEMPORAL, s.G, nullptr, s.G, nb, T, st))) return rc;
+            KASF_MARK();
             if ((rc = launch_former_module(blob, l, KASF_KIND_BONE, KASF_MODE_SPATIAL, bone_src, s.XL, s.Bn, nb, T, st))) return rc;
+            KASF_MARK();
             if ((rc = launch_former_module(blob, l, KASF_KIND_BONE, KASF_MODE_TEMPORAL, s.Bn, s.XL, s.Bn, nb, T, st))) return rc;
+            KASF_MARK();
             if ((rc = launch_fusion(blob, l, s.A, s.G, s.Bn, s.X, tokens, st))) return rc;
+            KASF_MARK();
         }
         float* y = y_dev ? y_dev + (size_t)b0 * T * J * 3 : nullptr;
         float* rep = rep_dev ? rep_dev + (size_t)b0 * T * J * REP : nullptr;
         if ((rc = launch_head(blob, s.X, y, rep, tokens, st))) return rc;
+        KASF_MARK();
     }
+#undef KASF_MARK
     return KASF_OK;
+}
+
+int kasf_forward(const kasf_config* cfg, const void* packed_dev, const float* x_dev, float* y_dev, float* rep_dev,
+                 int B, void* ws_dev, size_t ws_bytes, void* stream) {
+    return forward_impl(cfg, packed_dev, x_dev, y_dev, rep_dev, B, ws_dev, ws_bytes, stream, nullptr);
+}
+
+int kasf_forward_timed(const kasf_config* cfg, const void* packed_dev, const float* x_dev, float* y_dev,
+                       float* rep_dev, int B, void* ws_dev, size_t ws_bytes, void* stream, void** events,
+                       int n_events) {
+    if (!events || n_events < kasf_forward_launches(cfg, B) + 1) return KASF_EINVAL;
+    return forward_impl(cfg, packed_dev, x_dev, y_dev, rep_dev, B, ws_dev, ws_bytes, stream, events);
+}
+
+void* kasf_event_create(void) {
+    cudaEvent_t e = nullptr;
+    return cudaEventCreate(&e) == cudaSuccess ? (void*)e : nullptr;
+}
+void kasf_event_destroy(void* e) {
+    if (e) cudaEventDestroy((cudaEvent_t)e);
+}
+float kasf_event_elapsed_ms(void* a, void* b) {
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, (cudaEvent_t)a, (cudaEvent_t)b) != cudaSuccess) return -1.f;
+    return ms;
 }
 
 int kasf_metrics(int T, const float* pred_dev, const float* pred_flip_dev, const float* gt_dev, const float* res_dev,
