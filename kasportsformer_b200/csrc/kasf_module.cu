@@ -70,7 +70,22 @@ __device__ __forceinline__ float wmax(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+// erf-GELU through tanh: 0.5 v (1 + erf(v / sqrt 2)) = 0.5 v (1 + tanh(v (a + b v^2 + c v^4))) with a minimax
+// fit of (a, b, c) (max abs deviation from the erf form 5.6e-5) and the hardware tanh (MUFU, rel. error
+// 2^-11).  The result is rounded to bf16 (2^-9) right after, so this is below the operand rounding; the
+// exact erff form costs ~5x the instructions and made the MLP epilogue the bottleneck of the kernel.
+__device__ __forceinline__ float gelu_erf(float v) {
+#ifdef KASF_EXACT_GELU
+    return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+#else
+    const float v2 = v * v;
+    const float pl = fmaf(v2, fmaf(v2, -0.0003828259195935171f, 0.03722352208203997f), 0.7972238404651819f);
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(v * pl));
+    const float hv = 0.5f * v;
+    return fmaf(hv, t, hv);
+#endif
+}
 
 // fp32 [128][128] tile with XOR-swizzled 16-byte chunks: conflict-free both for "warp per row" and
 // "thread per row" access.
@@ -202,6 +217,135 @@ __device__ __forceinline__ void epilogue_mixer(const ModParams& p, uint8_t* sm, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------- attention core
+// softmax(q k^T / 4) v for every (group, head) of the tile on warp-level tensor-core MMAs
+// (mma.sync.m16n8k16 bf16 -> fp32): the problems are 17x17 / TxT with head_dim 16 -- far too small and
+// too many for tcgen05 tiles.  Q [128 x 128] bf16 sits in the A tile (operand layout), K|V in AUX.  A work
+// item is (group, head, 16-query block); its output overwrites the Q block it consumed.
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int MAXNT>   // key tiles of 8 this instantiation can hold in registers (gsize <= 8 * MAXNT)
+__device__ __forceinline__ void attention_core_impl(uint8_t* sm, int warp, int lane, int gsize, int nrows) {
+    const uint32_t q_base = smem_u32(sm + SM_ATILE), kv_base = smem_u32(sm + SM_AUX);
+    const int ngroups = nrows / gsize;
+    const int mtiles = (gsize + 15) >> 4;
+    const int nkt = ((gsize + 15) >> 4) << 1;                     // key tiles, rounded up to pairs
+    const int items = ngroups * HEADS * mtiles;
+    const int g8 = lane >> 2, t4 = lane & 3, mi = lane >> 3, r8 = lane & 7;
+    const float scale = 0.25f * 1.4426950408889634f;              // head_dim^-1/2 * log2(e)
+#pragma unroll 1
+    for (int item = warp; item < items; item += CW) {
+        const int mt = item % mtiles, h = (item / mtiles) % HEADS, g = item / (mtiles * HEADS);
+        const int gr0 = g * gsize, m0 = gr0 + mt * 16;
+        uint32_t qa[4];
+        {
+            const int row = min(m0 + (mi & 1) * 8 + r8, 127);
+            ldsm_x4(q_base + tile_off_bf16(row, h * DH + (mi >> 1) * 8), qa);
+        }
+        float s[MAXNT][4];
+#pragma unroll
+        for (int nt = 0; nt < MAXNT; nt += 2) {
+            if (nt < nkt) {
+                uint32_t kb[4];
+                const int row = min(gr0 + 8 * (nt + (mi >> 1)) + r8, 127);
+                ldsm_x4(kv_base + f32_off(row, 2 * h + (mi & 1)), kb);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) s[nt][i] = 0.f, s[nt + 1][i] = 0.f;
+                mma_bf16_16816(s[nt], qa, kb[0], kb[1]);
+                mma_bf16_16816(s[nt + 1], qa, kb[2], kb[3]);
+            }
+        }
+        // ---- softmax over the keys of the group (rows g8 and g8+8 of the block), fp32
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < MAXNT; ++nt) {
+            if (nt < nkt) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int key = nt * 8 + t4 * 2 + (i & 1);
+                    s[nt][i] = key < gsize ? s[nt][i] * scale : -INFINITY;
+                }
+                mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+                mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+            }
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < MAXNT; ++nt) {
+            if (nt < nkt) {
+                s[nt][0] = ex2_approx(s[nt][0] - mx0);
+                s[nt][1] = ex2_approx(s[nt][1] - mx0);
+                s[nt][2] = ex2_approx(s[nt][2] - mx1);
+                s[nt][3] = ex2_approx(s[nt][3] - mx1);
+                l0 += s[nt][0] + s[nt][1];
+                l1 += s[nt][2] + s[nt][3];
+            }
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        // ---- O = P V  (P re-used from the score registers as the A operand)
+        float o[2][4];
+#pragma unroll
+        for (int dn = 0; dn < 2; ++dn)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[dn][i] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < MAXNT / 2; ++ks) {
+            if (2 * ks < nkt) {
+                uint32_t pa[4], vb[4];
+                pa[0] = pack_bf16(s[2 * ks][0], s[2 * ks][1]);
+                pa[1] = pack_bf16(s[2 * ks][2], s[2 * ks][3]);
+                pa[2] = pack_bf16(s[2 * ks + 1][0], s[2 * ks + 1][1]);
+                pa[3] = pack_bf16(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+                const int row = min(gr0 + 16 * ks + (mi & 1) * 8 + r8, 127);
+                ldsm_x4_t(kv_base + f32_off(row, 16 + 2 * h + (mi >> 1)), vb);
+                mma_bf16_16816(o[0], pa, vb[0], vb[1]);
+                mma_bf16_16816(o[1], pa, vb[2], vb[3]);
+            }
+        }
+        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+        const int qr0 = mt * 16 + g8, qr1 = qr0 + 8;               // query index inside the group
+#pragma unroll
+        for (int dn = 0; dn < 2; ++dn) {
+            const int col = h * DH + dn * 8 + t4 * 2;
+            if (qr0 < gsize)
+                *reinterpret_cast<uint32_t*>(sm + SM_ATILE + tile_off_bf16(gr0 + qr0, col)) = pack_bf16(o[dn][0] * i0, o[dn][1] * i0);
+            if (qr1 < gsize)
+                *reinterpret_cast<uint32_t*>(sm + SM_ATILE + tile_off_bf16(gr0 + qr1, col)) = pack_bf16(o[dn][2] * i1, o[dn][3] * i1);
+        }
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void attention_core(uint8_t* sm, int warp, int lane, int gsize, int nrows) {
+    if (MODE == KASF_MODE_SPATIAL || gsize <= 32) attention_core_impl<4>(sm, warp, lane, gsize, nrows);
+    else if (gsize <= 64) attention_core_impl<8>(sm, warp, lane, gsize, nrows);
+    else attention_core_impl<16>(sm, warp, lane, gsize, nrows);
+}
+
 // ----------------------------------------------------------------------------------------------
 template <int KIND, int MODE>
 __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const ModParams p) {
@@ -242,7 +386,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 for (int i = 0; i < NCH; ++i) {
                     const int ci = KIND == KASF_KIND_ATTENTION ? ORD_ATT[i] : (KIND == KASF_KIND_BONE ? ORD_BONE[i] : ORD_GCN[i]);
                     const uint32_t slot = cnt & 1, ph = (cnt >> 1) & 1;
-                    mbar_wait(&bars[B_EMPTY0 + slot], ph ^ 1);
+                    while (!mbar_try_wait(&bars[B_EMPTY0 + slot], ph ^ 1)) __nanosleep(128);
                     mbar_arrive_expect_tx(&bars[B_FULL0 + slot], CHUNK_BYTES);
                     bulk_g2s(sm + SM_RING + slot * CHUNK_BYTES, chunks + (size_t)ci * CHUNK_BYTES, CHUNK_BYTES,
                              &bars[B_FULL0 + slot]);
@@ -286,8 +430,6 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 const long long left = (long long)p.B * J - (long long)tile * p.groups_per_tile;
                 nrows = (int)(left < p.groups_per_tile ? left : p.groups_per_tile) * p.T;
             }
-            const bool row_ok = e.row < nrows;
-            const int g0 = (e.row / gsize) * gsize;   // first row of this thread's group
 
             if (KIND == KASF_KIND_BONE) {
                 // ---- K,V from the limb stream: LN_limb(XL) Wkv^T
@@ -320,13 +462,14 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 }
                 mma.wait();
                 tc_fence_after();
-                // ---- K,V: TMEM -> bf16 smem (row pitch 512 B: K at bytes [0,256), V at [256,512))
+                // ---- Q,K,V: TMEM -> bf16 smem.  Q goes to the (now free) A tile in operand layout, where the
+                //      attention output later replaces it block by block; K|V go to AUX (row pitch 512 B).
 #pragma unroll
-                for (int kv = 0; kv < 2; ++kv)
+                for (int qkv = 0; qkv < 3; ++qkv)
 #pragma unroll
                     for (int b = 0; b < 2; ++b) {
                         uint32_t acc[32];
-                        tmem_ld32(e.tbase + (kv ? TM_V : TM_K) + e.half * 64 + b * 32, acc);
+                        tmem_ld32(e.tbase + qkv * 128 + e.half * 64 + b * 32, acc);
                         tmem_ld_wait();
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
@@ -335,70 +478,17 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                             pk.y = pack_bf16(__uint_as_float(acc[c * 8 + 2]), __uint_as_float(acc[c * 8 + 3]));
                             pk.z = pack_bf16(__uint_as_float(acc[c * 8 + 4]), __uint_as_float(acc[c * 8 + 5]));
                             pk.w = pack_bf16(__uint_as_float(acc[c * 8 + 6]), __uint_as_float(acc[c * 8 + 7]));
-                            const uint32_t chunk = kv * 16 + e.half * 8 + b * 4 + c;
-                            *reinterpret_cast<uint4*>(sm + SM_AUX + f32_off(e.row, chunk)) = pk;
+                            if (qkv == 0) {
+                                *reinterpret_cast<uint4*>(sm + SM_ATILE + tile_off_bf16(e.row, e.half * 64 + b * 32 + c * 8)) = pk;
+                            } else {
+                                const uint32_t chunk = (qkv - 1) * 16 + e.half * 8 + b * 4 + c;
+                                *reinterpret_cast<uint4*>(sm + SM_AUX + f32_off(e.row, chunk)) = pk;
+                            }
                         }
                     }
+                tc_fence_before();
                 csync();
-                // ---- attention core: this thread = query row e.row, heads [4*half, 4*half+4)
-#pragma unroll 1
-                for (int hh = 0; hh < 4; ++hh) {
-                    const int h = e.half * 4 + hh;
-                    uint32_t qr[16];
-                    tmem_ld16(e.tbase + TM_Q + h * DH, qr);
-                    tmem_ld_wait();
-                    float q[16], o[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        q[i] = __uint_as_float(qr[i]) * (0.25f * 1.4426950408889634f);   // d^-1/2 * log2(e)
-                        o[i] = 0.f;
-                    }
-                    float m = -INFINITY, l = 0.f;
-                    if (row_ok) {
-#pragma unroll 1
-                        for (int jj = 0; jj < gsize; ++jj) {
-                            const int jr = g0 + jj;
-                            const uint4 k0 = *reinterpret_cast<const uint4*>(sm + SM_AUX + f32_off(jr, 2 * h));
-                            const uint4 k1 = *reinterpret_cast<const uint4*>(sm + SM_AUX + f32_off(jr, 2 * h + 1));
-                            const uint32_t kw[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
-                            float s = 0.f;
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                s = fmaf(q[2 * i], __uint_as_float(kw[i] << 16), s);
-                                s = fmaf(q[2 * i + 1], __uint_as_float(kw[i] & 0xffff0000u), s);
-                            }
-                            if (s > m) {
-                                const float al = exp2f(m - s);
-                                l *= al;
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) o[i] *= al;
-                                m = s;
-                            }
-                            const float pj = exp2f(s - m);
-                            l += pj;
-                            const uint4 v0 = *reinterpret_cast<const uint4*>(sm + SM_AUX + f32_off(jr, 16 + 2 * h));
-                            const uint4 v1 = *reinterpret_cast<const uint4*>(sm + SM_AUX + f32_off(jr, 16 + 2 * h + 1));
-                            const uint32_t vw[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                o[2 * i] = fmaf(pj, __uint_as_float(vw[i] << 16), o[2 * i]);
-                                o[2 * i + 1] = fmaf(pj, __uint_as_float(vw[i] & 0xffff0000u), o[2 * i + 1]);
-                            }
-                        }
-                    }
-                    const float inv = row_ok ? 1.0f / l : 0.f;
-                    uint4 w0, w1;
-                    w0.x = pack_bf16(o[0] * inv, o[1] * inv);
-                    w0.y = pack_bf16(o[2] * inv, o[3] * inv);
-                    w0.z = pack_bf16(o[4] * inv, o[5] * inv);
-                    w0.w = pack_bf16(o[6] * inv, o[7] * inv);
-                    w1.x = pack_bf16(o[8] * inv, o[9] * inv);
-                    w1.y = pack_bf16(o[10] * inv, o[11] * inv);
-                    w1.z = pack_bf16(o[12] * inv, o[13] * inv);
-                    w1.w = pack_bf16(o[14] * inv, o[15] * inv);
-                    *reinterpret_cast<uint4*>(sm + SM_ATILE + tile_off_bf16(e.row, h * DH)) = w0;
-                    *reinterpret_cast<uint4*>(sm + SM_ATILE + tile_off_bf16(e.row, h * DH + 8)) = w1;
-                }
+                attention_core<MODE>(sm, warp, lane, gsize, nrows);
                 fence_proxy_async();
                 tc_fence_before();
                 csync();

@@ -126,11 +126,18 @@ def _attend(q: Tensor, k: Tensor, v: Tensor, mode: str, heads: int) -> Tensor:
     scale = d ** -0.5
     def split(t):  # [B,T,J,H,d] -> [B,H,T,J,d]
         return t.reshape(B, T, J, heads, d).permute(0, 3, 1, 2, 4)
-    q, k, v = split(q), split(_q(k)), split(_q(v))     # K/V tiles are kept in bf16 on chip
+    q, k, v = split(_q(q)), split(_q(k)), split(_q(v))   # Q/K/V tiles are kept in bf16 on chip
     if mode == "temporal":
         q, k, v = q.transpose(2, 3), k.transpose(2, 3), v.transpose(2, 3)   # [B,H,J,T,d]
-    att = torch.softmax((q @ k.transpose(-2, -1)) * scale, dim=-1)
-    o = att @ v
+    if EMULATE_BF16:
+        # the kernel feeds the un-normalised probabilities to the P.V tensor-core MMA in bf16 and
+        # divides by the fp32 row sum afterwards
+        sc = (q @ k.transpose(-2, -1)) * scale
+        p = torch.exp(sc - sc.amax(dim=-1, keepdim=True))
+        o = (_q(p) @ v) / p.sum(dim=-1, keepdim=True)
+    else:
+        att = torch.softmax((q @ k.transpose(-2, -1)) * scale, dim=-1)
+        o = att @ v
     if mode == "temporal":
         o = o.transpose(2, 3)                                               # [B,H,T,J,d]
     return o.permute(0, 2, 3, 1, 4).reshape(B, T, J, C)

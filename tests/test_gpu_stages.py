@@ -109,7 +109,7 @@ def test_former_module(br, kind, mode, T, B):
         assert (err_rows > 2e-3).float().mean().item() <= 0.005, f"{(err_rows > 2e-3).float().mean()}"
         assert err_rows.median().item() <= 5e-4
     else:
-        assert err_rows.max().item() <= 2e-3, f"emulated-oracle error {err_rows.max().item()}"
+        assert err_rows.max().item() <= 4e-3, f"emulated-oracle error {err_rows.max().item()}"
     err_f = ((out - ref).abs().amax(dim=-1).reshape(-1) / upd)
     assert err_f.quantile(0.99).item() <= 3e-2, f"fp32-oracle error {err_f.quantile(0.99).item()}"
 
