@@ -58,6 +58,8 @@ _SIGNATURES = {
                                           C.c_void_p]),
     "kasf_former_module": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "kasf_former_module_profiled": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "kasf_fusion": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "kasf_head": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -259,6 +261,25 @@ def former_module(cfg, blob, layer, kind, mode, v, XL=None, out=None):
         _check(lib().kasf_former_module(C.byref(c_config(cfg)), _ptr(blob), layer, KIND[kind], MODE[mode],
                                         _ptr(v), _ptr(XL), _ptr(out), B, _stream()), "kasf_former_module")
     return out
+
+
+PHASES = ["limb_kv", "load_ln1", "qkv_mma_wait", "qkv_drain", "attention", "proj_mma_wait", "similarity",
+          "aggregation", "v_mma_wait", "mixer_epilogue", "ln2", "mlp", "out_epilogue", "store"]
+
+
+def former_module_phases(cfg, blob, layer, kind, mode, v, XL=None):
+    """Run one module with the phase-cycle hook; returns {phase: mean cycles per tile per CTA}."""
+    _require_device(v.device)
+    out = torch.empty_like(v)
+    prof = torch.zeros(16, dtype=torch.int64, device=v.device)
+    with torch.cuda.device(v.device):
+        _check(lib().kasf_former_module_profiled(C.byref(c_config(cfg)), _ptr(blob), layer, KIND[kind], MODE[mode],
+                                                 _ptr(v), _ptr(XL), _ptr(out), v.shape[0], _stream(), _ptr(prof)),
+               "kasf_former_module_profiled")
+        torch.cuda.synchronize()
+    B, T = v.shape[0], v.shape[1]
+    tiles = (B * T + 6) // 7 if mode == "spatial" else (B * 17 + (128 // T) - 1) // (128 // T)
+    return {n: prof[i].item() / tiles for i, n in enumerate(PHASES)}, tiles
 
 
 def fusion(cfg, blob, layer, a, g, b):

@@ -8,20 +8,26 @@
 // grouping.  A persistent CTA owns a tile of <=128 group-aligned tokens for the whole module: the fp32
 // residual rows are read from HBM once and written once; everything in between stays on chip.
 //
+//   residual rows ........... cp.async (LDGSTS) gather into smem, then resident in TENSOR MEMORY (128 of
+//                             the 512 TMEM columns) for the whole module; updated in place by the epilogues
 //   dense projections ....... tcgen05.mma (bf16 x bf16 -> fp32 in TMEM), operands in 128B-swizzled smem;
 //                             weights arrive pre-swizzled by bulk async copies (TMA engine) through a
-//                             2-slot mbarrier ring fed by a dedicated producer warp
-//   LayerNorm ................ fp32, warp per row, two-pass statistics
-//   attention core ........... thread per query row, K/V (bf16) broadcast from smem, online softmax (fp32)
-//   temporal-GCN adjacency ... fp32 similarity on CUDA cores, exact 4th-largest selection with ">=" ties,
-//                             row-sum degrees, D^-1/2 A D^-1/2 applied as a sparse gather
-//   epilogues ................ thread per row straight out of TMEM (tcgen05.ld 32x32b)
+//                             3-slot mbarrier ring fed by a dedicated producer warp
+//   LayerNorm ............... fp32, two threads per row (thread = TMEM lane), exact two-pass statistics
+//   attention core .......... warp-level tensor-core MMAs (mma.sync m16n8k16 bf16) on Q/K/V bf16 tiles in
+//                             smem, fp32 softmax on the accumulator fragments
+//   temporal-GCN adjacency .. similarity z z^T to fp32 accuracy on tensor cores (3xTF32 split:
+//                             hi*hi + hi*lo + lo*hi), exact 4th-largest selection with multiplicity and ">="
+//                             ties, row-sum degrees, D^-1/2 A D^-1/2 applied as a sparse fp32 gather
+//   epilogues ............... thread per row straight out of TMEM (tcgen05.ld / tcgen05.st 32x32b)
 //
-// Shared memory map (bytes):   STASH  fp32 residual tile [128][128]             65536
-//                              AUX    K|V bf16 / z fp32 / MLP hidden tiles      65536
-//                              ATILE  bf16 A operand [128 x 128]                 32768
-//                              RING   2 x weight chunk [128 x 128] bf16          65536
-//                              barriers + adjacency scratch
+// Shared memory map (bytes):   AUX    row staging / K|V bf16 / z fp32 / MLP hidden tiles   65536
+//                              ATILE  bf16 A operand [128 x 128] (also Q, attention output)  32768
+//                              RING   3 x weight chunk [128 x 128] bf16                      98304
+//                              VEC    the module's fp32 vectors (LN, layer scale, biases)     10240
+//                              LN partials, adjacency bit masks, degrees, barriers
+// Tensor memory columns:       0..127 Q -> mixer output -> hidden chunk 0 | 128..255 K -> hidden chunk 1
+//                              256..383 V -> fc2 accumulator             | 384..511 residual rows X
 #include "kasf_internal.h"
 
 namespace kasf {
@@ -30,23 +36,25 @@ __constant__ int c_nbr[68] = KASF_NBR;
 __constant__ int c_deg[17] = KASF_DEG;
 
 constexpr int CW = 8;                         // compute warps
-constexpr int MOD_THREADS = (CW + 1) * 32;    // + producer warp
-constexpr uint32_t SM_STASH = 0;
-constexpr uint32_t SM_AUX = 65536;
-constexpr uint32_t SM_ATILE = 131072;
-constexpr uint32_t SM_RING = 163840;
-constexpr uint32_t SM_BARS = 229376;
-constexpr uint32_t SM_ADJ = SM_BARS + 256;        // u32 [128][4]
-constexpr uint32_t SM_ROWSUM = SM_ADJ + 2048;     // f32 [128]
-constexpr uint32_t SM_DEG = SM_ROWSUM + 512;      // u8  [128]
-constexpr uint32_t SM_TOTAL = SM_DEG + 128;       // 232320 <= 232448
+constexpr int MOD_THREADS = (CW + 4) * 32;    // + producer warpgroup (one working lane; register donor)
+constexpr int RING = 3;
+constexpr uint32_t SM_AUX = 0;
+constexpr uint32_t SM_ATILE = 65536;
+constexpr uint32_t SM_RING = 98304;
+constexpr uint32_t SM_VEC = SM_RING + RING * 32768;   // 196608
+constexpr uint32_t SM_PART = SM_VEC + 10240;          // float2 [128][2]
+constexpr uint32_t SM_ADJ = SM_PART + 2048;           // u32 [128][4]
+constexpr uint32_t SM_ROWSUM = SM_ADJ + 2048;         // f32 [128]
+constexpr uint32_t SM_DEG = SM_ROWSUM + 512;          // u8  [128]
+constexpr uint32_t SM_BARS = SM_DEG + 128;
+constexpr uint32_t SM_TOTAL = SM_BARS + 256;
 static_assert(SM_TOTAL <= 232448, "shared memory budget");
+static_assert(MOD_VEC_BYTES == 10240, "vector block size");
 
-// TMEM columns
-constexpr uint32_t TM_Q = 0, TM_K = 128, TM_V = 256, TM_MIX = 384;   // mixer phase
+constexpr uint32_t TM_MIX = 0, TM_K = 128, TM_V = 256, TM_X = 384;   // mixer phase (Q lives at TM_MIX)
 constexpr uint32_t TM_H0 = 0, TM_H1 = 128, TM_OUT = 256;            // MLP phase
 
-enum { B_FULL0 = 0, B_FULL1, B_EMPTY0, B_EMPTY1, B_MMA, B_HFULL0, B_HFULL1, B_HSFREE0, B_HSFREE1, B_OUT, B_COUNT };
+enum { B_FULL0 = 0, B_EMPTY0 = RING, B_MMA = 2 * RING, B_HFULL0, B_HFULL1, B_HSFREE0, B_HSFREE1, B_OUT, B_COUNT };
 
 struct ModParams {
     const uint8_t* mod;      // packed module (vector block + chunks)
@@ -56,20 +64,13 @@ struct ModParams {
     int B, T;
     int ntiles;
     int groups_per_tile;     // temporal: sequences per tile
+    unsigned long long* prof;   // optional [16] per-phase cycle counters (debug/profiling hook), else null
 };
 
 __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// the two warps (w, w+4) that share the rows of one TMEM lane quarter
+__device__ __forceinline__ void pair_sync(int warp) { asm volatile("bar.sync %0, 64;" ::"r"(2 + (warp & 3)) : "memory"); }
 
-__device__ __forceinline__ float wsum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ float wmax(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
 // erf-GELU through tanh: 0.5 v (1 + erf(v / sqrt 2)) = 0.5 v (1 + tanh(v (a + b v^2 + c v^4))) with a minimax
 // fit of (a, b, c) (max abs deviation from the erf form 5.6e-5) and the hardware tanh (MUFU, rel. error
 // 2^-11).  The result is rounded to bf16 (2^-9) right after, so this is below the operand rounding; the
@@ -119,109 +120,92 @@ __device__ __forceinline__ long long row_token(const ModParams& p, int tile, int
     }
 }
 
-// LayerNorm of the 128 rows of a tile.  SRC_GLOBAL: rows gathered from `src` by row_token (and stashed
-// in STASH when `stash` is set); otherwise rows come from STASH.  Writes the bf16 A operand tile and,
-// optionally, the fp32 normalised rows to AUX.
-template <int MODE, bool SRC_GLOBAL, bool STASH_IT, bool Z_TO_AUX>
-__device__ __forceinline__ void ln_tile(const ModParams& p, uint8_t* sm, int tile, const float* src,
-                                        const float* gamma, const float* beta, int warp, int lane) {
-    const float4 g4 = *reinterpret_cast<const float4*>(gamma + lane * 4);
-    const float4 b4 = *reinterpret_cast<const float4*>(beta + lane * 4);
-#pragma unroll 1
-    for (int rb = 0; rb < 16; rb += 4) {
-        float4 v[4];
-        bool ok[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int r = warp + CW * (rb + u);
-            if (SRC_GLOBAL) {
-                const long long tok = row_token<MODE>(p, tile, r);
-                ok[u] = tok >= 0;
-                v[u] = ok[u] ? *reinterpret_cast<const float4*>(src + tok * D + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            } else {
-                ok[u] = true;
-                v[u] = *reinterpret_cast<const float4*>(sm + SM_STASH + f32_off(r, lane));
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int r = warp + CW * (rb + u);
-            const float mean = wsum(v[u].x + v[u].y + v[u].z + v[u].w) * (1.0f / D);
-            const float dx = v[u].x - mean, dy = v[u].y - mean, dz = v[u].z - mean, dw = v[u].w - mean;
-            const float var = wsum(dx * dx + dy * dy + dz * dz + dw * dw) * (1.0f / D);
-            const float rstd = 1.0f / sqrtf(var + 1e-5f);
-            float4 z;
-            z.x = ok[u] ? dx * rstd * g4.x + b4.x : 0.f;
-            z.y = ok[u] ? dy * rstd * g4.y + b4.y : 0.f;
-            z.z = ok[u] ? dz * rstd * g4.z + b4.z : 0.f;
-            z.w = ok[u] ? dw * rstd * g4.w + b4.w : 0.f;
-            if (STASH_IT) *reinterpret_cast<float4*>(sm + SM_STASH + f32_off(r, lane)) = v[u];
-            if (Z_TO_AUX) *reinterpret_cast<float4*>(sm + SM_AUX + f32_off(r, lane)) = z;
-            uint2 pk;
-            pk.x = pack_bf16(z.x, z.y);
-            pk.y = pack_bf16(z.z, z.w);
-            *reinterpret_cast<uint2*>(sm + SM_ATILE + tile_off_bf16(r, lane * 4)) = pk;
-        }
+// gather the 128 rows of a tile into AUX (fp32, swizzled): one 16-byte cp.async per lane and row, all 16
+// rows of a warp in flight at once; padding rows are zero-filled.
+template <int MODE>
+__device__ __forceinline__ void load_rows(const ModParams& p, uint8_t* sm, int tile, const float* src, int warp, int lane) {
+#pragma unroll 4
+    for (int rr = 0; rr < 16; ++rr) {
+        const int r = warp + CW * rr;
+        const long long tok = row_token<MODE>(p, tile, r);
+        const float* g = src + (tok >= 0 ? tok : 0) * D + lane * 4;
+        cp_async16(sm + SM_AUX + f32_off(r, lane), g, tok >= 0 ? 16u : 0u);
     }
+    cp_async_commit();
 }
 
-// thread <-> (row, column half) mapping of the TMEM epilogues
+// thread <-> (row, column half) mapping of everything that touches tensor memory
 struct EpiMap {
     int row;          // tile row == TMEM lane
     int half;         // columns [64*half, 64*half+64)
+    int warp;
     uint32_t tbase;   // tmem base + lane offset
 };
 
-// x1 = stash + ls1 * mix   (written back to STASH in place), mix read from TMEM cols TM_MIX..+127
-template <int KIND, int MODE>
-__device__ __forceinline__ void epilogue_mixer(const ModParams& p, uint8_t* sm, const float* vec, const EpiMap& e,
-                                               int tile) {
-    // GCN: mix = relu(z + BN_node(acc + bU + rowsum*bV)); others: mix = acc + bproj
-    float bn_s = 1.f, bn_t = 0.f, rs = 0.f;
-    if (KIND == KASF_KIND_GRAPH) {
-        int node;
-        if (MODE == KASF_MODE_SPATIAL) node = e.row % J;
-        else node = e.row % p.T;
-        bn_s = vec[V_BNS + node];
-        bn_t = vec[V_BNT + node];
-        rs = *reinterpret_cast<const float*>(sm + SM_ROWSUM + e.row * 4);
+// LayerNorm statistics of a row whose two halves live in two threads (exact two-pass, fp32)
+__device__ __forceinline__ void ln_stats(uint8_t* sm, const EpiMap& e, const float (&xv)[64], float& mean, float& rstd) {
+    float2* part = reinterpret_cast<float2*>(sm + SM_PART);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 64; i += 4) s0 += xv[i], s1 += xv[i + 1], s2 += xv[i + 2], s3 += xv[i + 3];
+    part[e.row * 2 + e.half].x = (s0 + s1) + (s2 + s3);
+    pair_sync(e.warp);
+    mean = (part[e.row * 2].x + part[e.row * 2 + 1].x) * (1.0f / D);
+    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 64; i += 4) {
+        const float d0 = xv[i] - mean, d1 = xv[i + 1] - mean, d2 = xv[i + 2] - mean, d3 = xv[i + 3] - mean;
+        q0 = fmaf(d0, d0, q0), q1 = fmaf(d1, d1, q1), q2 = fmaf(d2, d2, q2), q3 = fmaf(d3, d3, q3);
     }
+    part[e.row * 2 + e.half].y = (q0 + q1) + (q2 + q3);
+    pair_sync(e.warp);
+    const float var = (part[e.row * 2].y + part[e.row * 2 + 1].y) * (1.0f / D);
+    rstd = 1.0f / sqrtf(var + 1e-5f);
+}
+
+// z = (x - mean) * rstd * gamma + beta for this thread's 64 columns -> bf16 A operand tile (+ fp32 copy in AUX)
+template <bool Z_TO_AUX>
+__device__ __forceinline__ void ln_write(uint8_t* sm, const EpiMap& e, const float (&xv)[64], float mean, float rstd,
+                                         const float* gamma, const float* beta, bool ok) {
+    const float nm = -mean * rstd;
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
-        uint32_t acc[32];
-        tmem_ld32(e.tbase + TM_MIX + e.half * 64 + b * 32, acc);
-        tmem_ld_wait();
+    for (int c = 0; c < 8; ++c) {
+        const int col = e.half * 64 + c * 8;
+        const float4 g0 = *reinterpret_cast<const float4*>(gamma + col), g1 = *reinterpret_cast<const float4*>(gamma + col + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(beta + col), b1 = *reinterpret_cast<const float4*>(beta + col + 4);
+        float z[8];
+        z[0] = fmaf(fmaf(xv[c * 8 + 0], rstd, nm), g0.x, b0.x);
+        z[1] = fmaf(fmaf(xv[c * 8 + 1], rstd, nm), g0.y, b0.y);
+        z[2] = fmaf(fmaf(xv[c * 8 + 2], rstd, nm), g0.z, b0.z);
+        z[3] = fmaf(fmaf(xv[c * 8 + 3], rstd, nm), g0.w, b0.w);
+        z[4] = fmaf(fmaf(xv[c * 8 + 4], rstd, nm), g1.x, b1.x);
+        z[5] = fmaf(fmaf(xv[c * 8 + 5], rstd, nm), g1.y, b1.y);
+        z[6] = fmaf(fmaf(xv[c * 8 + 6], rstd, nm), g1.z, b1.z);
+        z[7] = fmaf(fmaf(xv[c * 8 + 7], rstd, nm), g1.w, b1.w);
+        if (!ok) {
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-            const int col = e.half * 64 + b * 32 + c4 * 4;
-            float4* xs = reinterpret_cast<float4*>(sm + SM_STASH + f32_off(e.row, col >> 2));
-            float4 x = *xs;
-            const float4 ls = *reinterpret_cast<const float4*>(vec + V_LS1 + col);
-            const float4 bm = *reinterpret_cast<const float4*>(vec + V_BMIX + col);
-            float m0 = __uint_as_float(acc[c4 * 4 + 0]) + bm.x, m1 = __uint_as_float(acc[c4 * 4 + 1]) + bm.y,
-                  m2 = __uint_as_float(acc[c4 * 4 + 2]) + bm.z, m3 = __uint_as_float(acc[c4 * 4 + 3]) + bm.w;
-            if (KIND == KASF_KIND_GRAPH) {
-                const float4 bv = *reinterpret_cast<const float4*>(vec + V_BV + col);
-                const float4 z = *reinterpret_cast<const float4*>(sm + SM_AUX + f32_off(e.row, col >> 2));
-                m0 = fmaxf(z.x + ((m0 + rs * bv.x) * bn_s + bn_t), 0.f);
-                m1 = fmaxf(z.y + ((m1 + rs * bv.y) * bn_s + bn_t), 0.f);
-                m2 = fmaxf(z.z + ((m2 + rs * bv.z) * bn_s + bn_t), 0.f);
-                m3 = fmaxf(z.w + ((m3 + rs * bv.w) * bn_s + bn_t), 0.f);
-            }
-            x.x = fmaf(ls.x, m0, x.x);
-            x.y = fmaf(ls.y, m1, x.y);
-            x.z = fmaf(ls.z, m2, x.z);
-            x.w = fmaf(ls.w, m3, x.w);
-            *xs = x;
+            for (int i = 0; i < 8; ++i) z[i] = 0.f;
+        }
+        uint4 pk;
+        pk.x = pack_bf16(z[0], z[1]), pk.y = pack_bf16(z[2], z[3]), pk.z = pack_bf16(z[4], z[5]), pk.w = pack_bf16(z[6], z[7]);
+        *reinterpret_cast<uint4*>(sm + SM_ATILE + tile_off_bf16(e.row, col)) = pk;
+        if (Z_TO_AUX) {
+            *reinterpret_cast<float4*>(sm + SM_AUX + f32_off(e.row, col >> 2)) = make_float4(z[0], z[1], z[2], z[3]);
+            *reinterpret_cast<float4*>(sm + SM_AUX + f32_off(e.row, (col >> 2) + 1)) = make_float4(z[4], z[5], z[6], z[7]);
         }
     }
 }
 
-// ---------------------------------------------------------------------------------------------- attention core
-// softmax(q k^T / 4) v for every (group, head) of the tile on warp-level tensor-core MMAs
-// (mma.sync.m16n8k16 bf16 -> fp32): the problems are 17x17 / TxT with head_dim 16 -- far too small and
-// too many for tcgen05 tiles.  Q [128 x 128] bf16 sits in the A tile (operand layout), K|V in AUX.  A work
-// item is (group, head, 16-query block); its output overwrites the Q block it consumed.
+// this thread's 64 staged values of its row
+__device__ __forceinline__ void read_staged(const uint8_t* sm, const EpiMap& e, float (&xv)[64]) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        const float4 v = *reinterpret_cast<const float4*>(sm + SM_AUX + f32_off(e.row, e.half * 16 + c));
+        xv[c * 4] = v.x, xv[c * 4 + 1] = v.y, xv[c * 4 + 2] = v.z, xv[c * 4 + 3] = v.w;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- warp-level MMAs
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
@@ -235,13 +219,24 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void mma_tf32_1688(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 
-template <int MAXNT>   // key tiles of 8 this instantiation can hold in registers (gsize <= 8 * MAXNT)
+// ---------------------------------------------------------------------------------------------- attention core
+// softmax(q k^T / 4) v for every (group, head) of the tile on warp-level tensor-core MMAs: the problems are
+// 17x17 / TxT with head_dim 16 -- far too small and too many for tcgen05 tiles.  Q [128 x 128] bf16 sits in
+// the A tile (operand layout), K|V in AUX.  A work item is (group, head, 16-query block); its output
+// overwrites the Q block it consumed.  U independent items are interleaved per warp to hide the
+// ldmatrix -> mma -> shuffle -> ex2 -> mma dependency chain.
+template <int MAXNT, int U>   // MAXNT: key tiles of 8 held in registers (gsize <= 8 * MAXNT)
 __device__ __forceinline__ void attention_core_impl(uint8_t* sm, int warp, int lane, int gsize, int nrows) {
     const uint32_t q_base = smem_u32(sm + SM_ATILE), kv_base = smem_u32(sm + SM_AUX);
     const int ngroups = nrows / gsize;
@@ -251,99 +246,231 @@ __device__ __forceinline__ void attention_core_impl(uint8_t* sm, int warp, int l
     const int g8 = lane >> 2, t4 = lane & 3, mi = lane >> 3, r8 = lane & 7;
     const float scale = 0.25f * 1.4426950408889634f;              // head_dim^-1/2 * log2(e)
 #pragma unroll 1
-    for (int item = warp; item < items; item += CW) {
-        const int mt = item % mtiles, h = (item / mtiles) % HEADS, g = item / (mtiles * HEADS);
-        const int gr0 = g * gsize, m0 = gr0 + mt * 16;
-        uint32_t qa[4];
-        {
-            const int row = min(m0 + (mi & 1) * 8 + r8, 127);
-            ldsm_x4(q_base + tile_off_bf16(row, h * DH + (mi >> 1) * 8), qa);
+    for (int it0 = warp * U; it0 < items; it0 += CW * U) {
+        int h[U], gr0[U], mt[U];
+        bool live[U];
+        uint32_t qa[U][4];
+        float s[U][MAXNT][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            live[u] = it0 + u < items;
+            const int item = live[u] ? it0 + u : it0;
+            mt[u] = item % mtiles, h[u] = (item / mtiles) % HEADS;
+            gr0[u] = (item / (mtiles * HEADS)) * gsize;
+            const int row = min(gr0[u] + mt[u] * 16 + (mi & 1) * 8 + r8, 127);
+            ldsm_x4(q_base + tile_off_bf16(row, h[u] * DH + (mi >> 1) * 8), qa[u]);
         }
-        float s[MAXNT][4];
 #pragma unroll
         for (int nt = 0; nt < MAXNT; nt += 2) {
             if (nt < nkt) {
-                uint32_t kb[4];
-                const int row = min(gr0 + 8 * (nt + (mi >> 1)) + r8, 127);
-                ldsm_x4(kv_base + f32_off(row, 2 * h + (mi & 1)), kb);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) s[nt][i] = 0.f, s[nt + 1][i] = 0.f;
-                mma_bf16_16816(s[nt], qa, kb[0], kb[1]);
-                mma_bf16_16816(s[nt + 1], qa, kb[2], kb[3]);
+                for (int u = 0; u < U; ++u) {
+                    uint32_t kb[4];
+                    const int row = min(gr0[u] + 8 * (nt + (mi >> 1)) + r8, 127);
+                    ldsm_x4(kv_base + f32_off(row, 2 * h[u] + (mi & 1)), kb);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) s[u][nt][i] = 0.f, s[u][nt + 1][i] = 0.f;
+                    mma_bf16_16816(s[u][nt], qa[u], kb[0], kb[1]);
+                    mma_bf16_16816(s[u][nt + 1], qa[u], kb[2], kb[3]);
+                }
             }
         }
         // ---- softmax over the keys of the group (rows g8 and g8+8 of the block), fp32
-        float mx0 = -INFINITY, mx1 = -INFINITY;
+        float l0[U], l1[U];
 #pragma unroll
-        for (int nt = 0; nt < MAXNT; ++nt) {
-            if (nt < nkt) {
+        for (int u = 0; u < U; ++u) {
+            float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int key = nt * 8 + t4 * 2 + (i & 1);
-                    s[nt][i] = key < gsize ? s[nt][i] * scale : -INFINITY;
+            for (int nt = 0; nt < MAXNT; ++nt) {
+                if (nt < nkt) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int key = nt * 8 + t4 * 2 + (i & 1);
+                        s[u][nt][i] = key < gsize ? s[u][nt][i] * scale : -INFINITY;
+                    }
+                    mx0 = fmaxf(mx0, fmaxf(s[u][nt][0], s[u][nt][1]));
+                    mx1 = fmaxf(mx1, fmaxf(s[u][nt][2], s[u][nt][3]));
                 }
-                mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
-                mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
             }
-        }
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        float l0 = 0.f, l1 = 0.f;
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+            float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-        for (int nt = 0; nt < MAXNT; ++nt) {
-            if (nt < nkt) {
-                s[nt][0] = ex2_approx(s[nt][0] - mx0);
-                s[nt][1] = ex2_approx(s[nt][1] - mx0);
-                s[nt][2] = ex2_approx(s[nt][2] - mx1);
-                s[nt][3] = ex2_approx(s[nt][3] - mx1);
-                l0 += s[nt][0] + s[nt][1];
-                l1 += s[nt][2] + s[nt][3];
+            for (int nt = 0; nt < MAXNT; ++nt) {
+                if (nt < nkt) {
+                    s[u][nt][0] = ex2_approx(s[u][nt][0] - mx0);
+                    s[u][nt][1] = ex2_approx(s[u][nt][1] - mx0);
+                    s[u][nt][2] = ex2_approx(s[u][nt][2] - mx1);
+                    s[u][nt][3] = ex2_approx(s[u][nt][3] - mx1);
+                    a0 += s[u][nt][0] + s[u][nt][1];
+                    a1 += s[u][nt][2] + s[u][nt][3];
+                }
             }
+            a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+            a0 += __shfl_xor_sync(0xffffffffu, a0, 2);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+            l0[u] = a0, l1[u] = a1;
         }
-        l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-        l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
         // ---- O = P V  (P re-used from the score registers as the A operand)
-        float o[2][4];
+        float o[U][2][4];
 #pragma unroll
-        for (int dn = 0; dn < 2; ++dn)
+        for (int u = 0; u < U; ++u)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) o[dn][i] = 0.f;
+            for (int dn = 0; dn < 2; ++dn)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o[u][dn][i] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < MAXNT / 2; ++ks) {
             if (2 * ks < nkt) {
-                uint32_t pa[4], vb[4];
-                pa[0] = pack_bf16(s[2 * ks][0], s[2 * ks][1]);
-                pa[1] = pack_bf16(s[2 * ks][2], s[2 * ks][3]);
-                pa[2] = pack_bf16(s[2 * ks + 1][0], s[2 * ks + 1][1]);
-                pa[3] = pack_bf16(s[2 * ks + 1][2], s[2 * ks + 1][3]);
-                const int row = min(gr0 + 16 * ks + (mi & 1) * 8 + r8, 127);
-                ldsm_x4_t(kv_base + f32_off(row, 16 + 2 * h + (mi >> 1)), vb);
-                mma_bf16_16816(o[0], pa, vb[0], vb[1]);
-                mma_bf16_16816(o[1], pa, vb[2], vb[3]);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    uint32_t pa[4], vb[4];
+                    pa[0] = pack_bf16(s[u][2 * ks][0], s[u][2 * ks][1]);
+                    pa[1] = pack_bf16(s[u][2 * ks][2], s[u][2 * ks][3]);
+                    pa[2] = pack_bf16(s[u][2 * ks + 1][0], s[u][2 * ks + 1][1]);
+                    pa[3] = pack_bf16(s[u][2 * ks + 1][2], s[u][2 * ks + 1][3]);
+                    const int row = min(gr0[u] + 16 * ks + (mi & 1) * 8 + r8, 127);
+                    ldsm_x4_t(kv_base + f32_off(row, 16 + 2 * h[u] + (mi >> 1)), vb);
+                    mma_bf16_16816(o[u][0], pa, vb[0], vb[1]);
+                    mma_bf16_16816(o[u][1], pa, vb[2], vb[3]);
+                }
             }
         }
-        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-        const int qr0 = mt * 16 + g8, qr1 = qr0 + 8;               // query index inside the group
 #pragma unroll
-        for (int dn = 0; dn < 2; ++dn) {
-            const int col = h * DH + dn * 8 + t4 * 2;
-            if (qr0 < gsize)
-                *reinterpret_cast<uint32_t*>(sm + SM_ATILE + tile_off_bf16(gr0 + qr0, col)) = pack_bf16(o[dn][0] * i0, o[dn][1] * i0);
-            if (qr1 < gsize)
-                *reinterpret_cast<uint32_t*>(sm + SM_ATILE + tile_off_bf16(gr0 + qr1, col)) = pack_bf16(o[dn][2] * i1, o[dn][3] * i1);
+        for (int u = 0; u < U; ++u) {
+            const float i0 = 1.0f / l0[u], i1 = 1.0f / l1[u];
+            const int qr0 = mt[u] * 16 + g8, qr1 = qr0 + 8;           // query index inside the group
+#pragma unroll
+            for (int dn = 0; dn < 2; ++dn) {
+                const int col = h[u] * DH + dn * 8 + t4 * 2;
+                if (live[u] && qr0 < gsize)
+                    *reinterpret_cast<uint32_t*>(sm + SM_ATILE + tile_off_bf16(gr0[u] + qr0, col)) =
+                        pack_bf16(o[u][dn][0] * i0, o[u][dn][1] * i0);
+                if (live[u] && qr1 < gsize)
+                    *reinterpret_cast<uint32_t*>(sm + SM_ATILE + tile_off_bf16(gr0[u] + qr1, col)) =
+                        pack_bf16(o[u][dn][2] * i1, o[u][dn][3] * i1);
+            }
         }
     }
 }
 
 template <int MODE>
 __device__ __forceinline__ void attention_core(uint8_t* sm, int warp, int lane, int gsize, int nrows) {
-    if (MODE == KASF_MODE_SPATIAL || gsize <= 32) attention_core_impl<4>(sm, warp, lane, gsize, nrows);
-    else if (gsize <= 64) attention_core_impl<8>(sm, warp, lane, gsize, nrows);
-    else attention_core_impl<16>(sm, warp, lane, gsize, nrows);
+    if (MODE == KASF_MODE_SPATIAL || gsize <= 32) attention_core_impl<4, 2>(sm, warp, lane, gsize, nrows);
+    else if (gsize <= 64) attention_core_impl<8, 1>(sm, warp, lane, gsize, nrows);
+    else attention_core_impl<16, 1>(sm, warp, lane, gsize, nrows);
+}
+
+// ---------------------------------------------------------------------------------------------- temporal adjacency
+// S = z z^T per sequence to fp32 accuracy on tensor cores (3xTF32: the operand is split into the 19 bits the
+// tensor core reads and the exact fp32 remainder; hi*hi + hi*lo + lo*hi), then per row the 4th largest value
+// with multiplicity (torch.topk, graph.py:109) and A_ij = S_ij >= thr (:111).  Work item = (sequence,
+// 16-row block); the row's bit mask and degree go to smem.
+template <int MAXNT>
+__device__ __forceinline__ void similarity_topk_impl(uint8_t* sm, int warp, int lane, int T, int nrows) {
+    uint32_t* adj = reinterpret_cast<uint32_t*>(sm + SM_ADJ);
+    uint8_t* degs = sm + SM_DEG;
+    const int ngroups = nrows / T, mtiles = (T + 15) >> 4, nkt = (T + 7) >> 3;
+    const int g8 = lane >> 2, t4 = lane & 3;
+#pragma unroll 1
+    for (int item = warp; item < ngroups * mtiles; item += CW) {
+        const int g = item / mtiles, mt = item - g * mtiles;
+        const int gr0 = g * T, m0 = gr0 + mt * 16;
+        const int ra = min(m0 + g8, 127), rb = min(m0 + g8 + 8, 127);
+        float s[MAXNT][4];
+#pragma unroll
+        for (int nt = 0; nt < MAXNT; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s[nt][i] = 0.f;
+#pragma unroll 2
+        for (int ks = 0; ks < 16; ++ks) {           // K = 128 in steps of 8
+            // A fragment: (row g8 | g8+8, k = 8 ks + t4 | + 4)
+            float av[4];
+            av[0] = *reinterpret_cast<const float*>(sm + SM_AUX + f32_off(ra, 2 * ks) + t4 * 4);
+            av[1] = *reinterpret_cast<const float*>(sm + SM_AUX + f32_off(rb, 2 * ks) + t4 * 4);
+            av[2] = *reinterpret_cast<const float*>(sm + SM_AUX + f32_off(ra, 2 * ks + 1) + t4 * 4);
+            av[3] = *reinterpret_cast<const float*>(sm + SM_AUX + f32_off(rb, 2 * ks + 1) + t4 * 4);
+            uint32_t ah[4], al[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ah[i] = __float_as_uint(av[i]) & 0xffffe000u;
+                al[i] = __float_as_uint(av[i] - __uint_as_float(ah[i]));
+            }
+#pragma unroll
+            for (int nt = 0; nt < MAXNT; ++nt) {
+                if (nt < nkt) {
+                    // B fragment: (k = 8 ks + t4 | + 4, n = key 8 nt + g8)
+                    const int rj = min(gr0 + 8 * nt + g8, 127);
+                    const float b0 = *reinterpret_cast<const float*>(sm + SM_AUX + f32_off(rj, 2 * ks) + t4 * 4);
+                    const float b1 = *reinterpret_cast<const float*>(sm + SM_AUX + f32_off(rj, 2 * ks + 1) + t4 * 4);
+                    const uint32_t bh0 = __float_as_uint(b0) & 0xffffe000u, bh1 = __float_as_uint(b1) & 0xffffe000u;
+                    const uint32_t bl0 = __float_as_uint(b0 - __uint_as_float(bh0));
+                    const uint32_t bl1 = __float_as_uint(b1 - __uint_as_float(bh1));
+                    mma_tf32_1688(s[nt], al, bh0, bh1);
+                    mma_tf32_1688(s[nt], ah, bl0, bl1);
+                    mma_tf32_1688(s[nt], ah, bh0, bh1);
+                }
+            }
+        }
+        // ---- rows g8 (values s[nt][0..1]) and g8+8 (s[nt][2..3]); a row is spread over the 4 lanes of a quad
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow) {
+            float v[MAXNT][2];
+#pragma unroll
+            for (int nt = 0; nt < MAXNT; ++nt)
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+                    v[nt][i] = (nt < nkt && nt * 8 + t4 * 2 + i < T) ? s[nt][hrow * 2 + i] : -INFINITY;
+            float thr = 0.f;
+#pragma unroll 1
+            for (int it = 0; it < 4; ++it) {
+                float lm = -INFINITY;
+#pragma unroll
+                for (int nt = 0; nt < MAXNT; ++nt) lm = fmaxf(lm, fmaxf(v[nt][0], v[nt][1]));
+                thr = fmaxf(lm, __shfl_xor_sync(0xffffffffu, lm, 1));
+                thr = fmaxf(thr, __shfl_xor_sync(0xffffffffu, thr, 2));
+                const unsigned owners = (__ballot_sync(0xffffffffu, lm == thr) >> (g8 * 4)) & 0xfu;
+                if (t4 == __ffs(owners) - 1) {          // remove exactly one instance of the maximum
+                    bool done = false;
+#pragma unroll
+                    for (int nt = 0; nt < MAXNT; ++nt)
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+                            if (!done && v[nt][i] == thr) v[nt][i] = -INFINITY, done = true;
+                }
+            }
+            // adjacency bits of this row: key 8 nt + 2 t4 + i
+            const int row = m0 + g8 + hrow * 8;
+            int deg = 0;
+#pragma unroll
+            for (int w = 0; w < (MAXNT + 3) / 4; ++w) {
+                uint32_t bits = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int nt = w * 4 + q;
+                    if (nt < MAXNT && nt < nkt) {
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+                            if (nt * 8 + t4 * 2 + i < T && s[nt][hrow * 2 + i] >= thr) bits |= 1u << (q * 8 + t4 * 2 + i);
+                    }
+                }
+                bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
+                bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
+                deg += __popc(bits);
+                if (t4 == 0 && row < gr0 + T) adj[row * 4 + w] = bits;
+            }
+            if (t4 == 0 && row < gr0 + T) degs[row] = (uint8_t)deg;
+        }
+    }
+}
+
+__device__ __forceinline__ void similarity_topk(uint8_t* sm, int warp, int lane, int T, int nrows) {
+    if (T <= 32) similarity_topk_impl<4>(sm, warp, lane, T, nrows);
+    else if (T <= 64) similarity_topk_impl<8>(sm, warp, lane, T, nrows);
+    else similarity_topk_impl<16>(sm, warp, lane, T, nrows);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -353,7 +480,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM_BARS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + SM_BARS + B_COUNT * 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const float* vec = reinterpret_cast<const float*>(p.mod);
+    const float* vec = reinterpret_cast<const float*>(sm + SM_VEC);
     const uint8_t* chunks = p.mod + MOD_VEC_BYTES;
 
     if (tid == 0) {
@@ -365,6 +492,8 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
+    for (int i = tid; i < V_FLOATS / 4; i += MOD_THREADS)   // the module's fp32 vectors, once per CTA
+        reinterpret_cast<float4*>(sm + SM_VEC)[i] = reinterpret_cast<const float4*>(p.mod)[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -377,31 +506,34 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
     constexpr int ORD_BONE[12] = {1, 2, 0, 3, 4, 5, 8, 6, 9, 7, 10, 11};
     constexpr int ORD_GCN[12] = {0, 1, 4, 5, 8, 6, 9, 7, 10, 11, 0, 0};
 
-    if (warp == CW) {
-        // ===================== producer warp: stream weight chunks through the ring =====================
-        if (lane == 0) {
-            uint32_t cnt = 0;
+    if (warp >= CW) {
+        // ===================== producer warpgroup: stream weight chunks through the ring =====================
+        // (hands its registers to the compute warpgroups: 8 x 232 + 4 x 40 regs per thread fit the file)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == CW && lane == 0) {
+            uint32_t slot = 0, ph = 0;
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
 #pragma unroll 1
                 for (int i = 0; i < NCH; ++i) {
                     const int ci = KIND == KASF_KIND_ATTENTION ? ORD_ATT[i] : (KIND == KASF_KIND_BONE ? ORD_BONE[i] : ORD_GCN[i]);
-                    const uint32_t slot = cnt & 1, ph = (cnt >> 1) & 1;
-                    while (!mbar_try_wait(&bars[B_EMPTY0 + slot], ph ^ 1)) __nanosleep(128);
+                    while (!mbar_try_wait(&bars[B_EMPTY0 + slot], ph ^ 1)) __nanosleep(64);
                     mbar_arrive_expect_tx(&bars[B_FULL0 + slot], CHUNK_BYTES);
                     bulk_g2s(sm + SM_RING + slot * CHUNK_BYTES, chunks + (size_t)ci * CHUNK_BYTES, CHUNK_BYTES,
                              &bars[B_FULL0 + slot]);
-                    ++cnt;
+                    if (++slot == RING) slot = 0, ph ^= 1;
                 }
             }
         }
         __syncwarp();
     } else {
         // ===================== compute warps =====================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
         EpiMap e;
         e.row = (warp & 3) * 32 + lane;
         e.half = warp >> 2;
+        e.warp = warp;
         e.tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        uint32_t ccnt = 0;   // chunks consumed (meaningful in thread 0)
+        uint32_t cslot = 0, cph = 0;   // ring read position (meaningful in thread 0)
         WaitBar mma{&bars[B_MMA], 0}, hfull0{&bars[B_HFULL0], 0}, hfull1{&bars[B_HFULL1], 0},
             hsfree0{&bars[B_HSFREE0], 0}, hsfree1{&bars[B_HSFREE1], 0}, outb{&bars[B_OUT], 0};
         const uint32_t a_addr = smem_u32(sm + SM_ATILE);
@@ -410,14 +542,22 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
 
         // issue one weight chunk's MMA: D[tmem col] (+)= A(a_smem) * ring[slot]^T ; frees the slot when done
         auto mma_chunk = [&](uint32_t tcol, uint32_t a_smem, bool acc) {
-            const uint32_t slot = ccnt & 1, ph = (ccnt >> 1) & 1;
-            mbar_wait(&bars[B_FULL0 + slot], ph);
+            mbar_wait(&bars[B_FULL0 + cslot], cph);
             tc_fence_after();
-            umma_tile_k128(tmem + tcol, a_smem, ring_addr + slot * CHUNK_BYTES, 128, acc);
-            tc_commit(&bars[B_EMPTY0 + slot]);
-            ++ccnt;
+            umma_tile_k128(tmem + tcol, a_smem, ring_addr + cslot * CHUNK_BYTES, 128, acc);
+            tc_commit(&bars[B_EMPTY0 + cslot]);
+            if (++cslot == RING) cslot = 0, cph ^= 1;
         };
 
+        long long pt0 = p.prof ? clock64() : 0;
+#define PMARK(k)                                                      \
+    do {                                                              \
+        if (p.prof && tid == 0) {                                     \
+            const long long pt1 = clock64();                          \
+            atomicAdd(p.prof + (k), (unsigned long long)(pt1 - pt0)); \
+            pt0 = pt1;                                                \
+        }                                                             \
+    } while (0)
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
             // rows of this tile that carry tokens, and the group geometry
             int gsize, nrows;
@@ -430,30 +570,57 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 const long long left = (long long)p.B * J - (long long)tile * p.groups_per_tile;
                 nrows = (int)(left < p.groups_per_tile ? left : p.groups_per_tile) * p.T;
             }
+            const bool row_ok = e.row < nrows;
+            float xv[64];
+            float mean, rstd;
 
             if (KIND == KASF_KIND_BONE) {
                 // ---- K,V from the limb stream: LN_limb(XL) Wkv^T
-                ln_tile<MODE, true, false, false>(p, sm, tile, p.xl, vec + V_NLW, vec + V_NLB, warp, lane);
+                load_rows<MODE>(p, sm, tile, p.xl, warp, lane);
+                cp_async_wait_all();
+                csync();
+                read_staged(sm, e, xv);
+                ln_stats(sm, e, xv, mean, rstd);
+                ln_write<false>(sm, e, xv, mean, rstd, vec + V_NLW, vec + V_NLB, row_ok);
                 fence_proxy_async();
                 tc_fence_before();
-                csync();
+                csync();                                   // AUX is free again, the A tile is complete
                 if (tid == 0) {
+                    tc_fence_after();
                     mma_chunk(TM_K, a_addr, false);
                     mma_chunk(TM_V, a_addr, false);
                     tc_commit(&bars[B_MMA]);
                 }
-                mma.wait();   // A tile free again (and K,V complete)
+                load_rows<MODE>(p, sm, tile, p.in, warp, lane);   // overlaps the K,V MMAs
+                mma.wait();                                // A tile free again (and K,V complete)
                 tc_fence_after();
+                PMARK(0);
+            } else {
+                load_rows<MODE>(p, sm, tile, p.in, warp, lane);
             }
-            // ---- load residual rows, stash them, LN1 -> A operand
-            ln_tile<MODE, true, true, KIND == KASF_KIND_GRAPH>(p, sm, tile, p.in, vec + V_N1W, vec + V_N1B, warp, lane);
+            // ---- residual rows: smem staging -> registers -> tensor memory (resident); LN1 -> A operand
+            cp_async_wait_all();
+            csync();
+            read_staged(sm, e, xv);
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                uint32_t xr[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) xr[i] = __float_as_uint(xv[b * 32 + i]);
+                tmem_st32(e.tbase + TM_X + e.half * 64 + b * 32, xr);
+            }
+            ln_stats(sm, e, xv, mean, rstd);
+            ln_write<KIND == KASF_KIND_GRAPH>(sm, e, xv, mean, rstd, vec + V_N1W, vec + V_N1B, row_ok);
+            tmem_st_wait();
             fence_proxy_async();
             tc_fence_before();
             csync();
+            PMARK(1);
 
             if (KIND != KASF_KIND_GRAPH) {
                 if (tid == 0) {
-                    mma_chunk(TM_Q, a_addr, false);
+                    tc_fence_after();
+                    mma_chunk(TM_MIX, a_addr, false);          // Q
                     if (KIND == KASF_KIND_ATTENTION) {
                         mma_chunk(TM_K, a_addr, false);
                         mma_chunk(TM_V, a_addr, false);
@@ -462,6 +629,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 }
                 mma.wait();
                 tc_fence_after();
+                PMARK(2);
                 // ---- Q,K,V: TMEM -> bf16 smem.  Q goes to the (now free) A tile in operand layout, where the
                 //      attention output later replaces it block by block; K|V go to AUX (row pitch 512 B).
 #pragma unroll
@@ -488,160 +656,150 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                     }
                 tc_fence_before();
                 csync();
+                PMARK(3);
                 attention_core<MODE>(sm, warp, lane, gsize, nrows);
                 fence_proxy_async();
-                tc_fence_before();
                 csync();
+                PMARK(4);
                 if (tid == 0) {
-                    mma_chunk(TM_MIX, a_addr, false);   // output projection
+                    tc_fence_after();
+                    mma_chunk(TM_MIX, a_addr, false);   // output projection (Q's columns are dead)
                     tc_commit(&bars[B_MMA]);
                 }
                 mma.wait();
                 tc_fence_after();
+                PMARK(5);
             } else {
                 // ================= GCN mixer =================
                 if (tid == 0) {
+                    tc_fence_after();
                     mma_chunk(TM_MIX, a_addr, false);   // U z
                     tc_commit(&bars[B_MMA]);
                 }
-                float* rowsum = reinterpret_cast<float*>(sm + SM_ROWSUM);
                 if (MODE == KASF_MODE_TEMPORAL) {
-                    // ---- similarity S = z z^T per sequence (fp32), 4th-largest threshold, adjacency bits
-                    uint32_t* adj = reinterpret_cast<uint32_t*>(sm + SM_ADJ);
-                    uint8_t* degs = sm + SM_DEG;
-                    const int T = p.T;
-                    const int nib = (T + 3) >> 2;
-                    const int ngroups = nrows / T;
-#pragma unroll 1
-                    for (int item = warp; item < ngroups * nib; item += CW) {
-                        const int g = item / nib, ib = item - g * nib;
-                        const int gr0 = g * T, i0 = gr0 + ib * 4, gend = gr0 + T;
-                        float s[4][4];
-#pragma unroll
-                        for (int a = 0; a < 4; ++a)
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) s[a][q] = 0.f;
-                        int ri[4];
-#pragma unroll
-                        for (int a = 0; a < 4; ++a) ri[a] = min(i0 + a, gend - 1);
-#pragma unroll 2
-                        for (int kc = 0; kc < 32; ++kc) {
-                            float4 zi[4];
-#pragma unroll
-                            for (int a = 0; a < 4; ++a)
-                                zi[a] = *reinterpret_cast<const float4*>(sm + SM_AUX + f32_off(ri[a], kc));
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const int j = lane + 32 * q;
-                                if (32 * q < T) {
-                                    const int jr = gr0 + min(j, T - 1);
-                                    const float4 zj = *reinterpret_cast<const float4*>(sm + SM_AUX + f32_off(jr, kc));
-#pragma unroll
-                                    for (int a = 0; a < 4; ++a)
-                                        s[a][q] = fmaf(zi[a].w, zj.w, fmaf(zi[a].z, zj.z, fmaf(zi[a].y, zj.y, fmaf(zi[a].x, zj.x, s[a][q]))));
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int a = 0; a < 4; ++a) {
-                            if (i0 + a >= gend) break;   // warp-uniform
-                            float v[4];
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) v[q] = (lane + 32 * q < T) ? s[a][q] : -INFINITY;
-                            float thr = 0.f;
-                            // k-th largest with multiplicity (torch.topk semantics), k = 4
-#pragma unroll 1
-                            for (int it = 0; it < 4; ++it) {
-                                const float lm = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
-                                thr = wmax(lm);
-                                const unsigned owners = __ballot_sync(0xffffffffu, lm == thr);
-                                if (lane == __ffs(owners) - 1) {   // remove exactly one instance
-                                    if (v[0] == thr) v[0] = -INFINITY;
-                                    else if (v[1] == thr) v[1] = -INFINITY;
-                                    else if (v[2] == thr) v[2] = -INFINITY;
-                                    else v[3] = -INFINITY;
-                                }
-                            }
-                            int deg = 0;
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const unsigned bits = __ballot_sync(0xffffffffu, (lane + 32 * q < T) && s[a][q] >= thr);
-                                deg += __popc(bits);
-                                if (lane == 0) adj[(i0 + a) * 4 + q] = bits;
-                            }
-                            if (lane == 0) degs[i0 + a] = (uint8_t)deg;
-                        }
-                    }
+                    similarity_topk(sm, warp, lane, p.T, nrows);
                     csync();
+                    PMARK(6);
                 }
-                mma.wait();   // U z done: the A tile may be overwritten (temporal: hidden behind the similarity)
-                tc_fence_after();
-                // ---- aggregation  agg_i = sum_j A_ij / sqrt(d_i d_j) * z_j   (warp per row) -> bf16 A tile
-#pragma unroll 1
-                for (int rr = 0; rr < 16; ++rr) {
-                    const int r = warp + CW * rr;
-                    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    float rs = 0.f;
-                    if (r < nrows) {
-                        if (MODE == KASF_MODE_SPATIAL) {
-                            const int j = r % J, base = r - j;
-                            const float di = 1.0f / sqrtf((float)c_deg[j]);
+                // ---- aggregation  agg_i = sum_j A_ij / sqrt(d_i d_j) * z_j : this thread's 64 columns of its row
+                float rs = 0.f;
 #pragma unroll
-                            for (int n = 0; n < 4; ++n) {
-                                const int nb = c_nbr[j * 4 + n];
-                                if (nb >= 0) {
-                                    const float cf = di * (1.0f / sqrtf((float)c_deg[nb]));
-                                    const float4 z = *reinterpret_cast<const float4*>(sm + SM_AUX + f32_off(base + nb, lane));
-                                    a4.x = fmaf(cf, z.x, a4.x), a4.y = fmaf(cf, z.y, a4.y);
-                                    a4.z = fmaf(cf, z.z, a4.z), a4.w = fmaf(cf, z.w, a4.w);
-                                    rs += cf;
-                                }
-                            }
-                        } else {
-                            const uint32_t* adj = reinterpret_cast<const uint32_t*>(sm + SM_ADJ);
-                            const uint8_t* degs = sm + SM_DEG;
-                            const int gr0 = (r / p.T) * p.T;
-                            const float di = 1.0f / sqrtf((float)degs[r]);
+                for (int i = 0; i < 64; ++i) xv[i] = 0.f;
+                if (row_ok) {
+                    if (MODE == KASF_MODE_SPATIAL) {
+                        const int j = e.row % J, base = e.row - j;
+                        const float di = 1.0f / sqrtf((float)c_deg[j]);
 #pragma unroll 1
-                            for (int q = 0; q < 4; ++q) {
-                                unsigned bits = (32 * q < p.T) ? adj[r * 4 + q] : 0u;
-                                while (bits) {
-                                    const int jb = __ffs(bits) - 1;
-                                    bits &= bits - 1;
-                                    const int jr = gr0 + 32 * q + jb;
-                                    const float cf = di * (1.0f / sqrtf((float)degs[jr]));
-                                    const float4 z = *reinterpret_cast<const float4*>(sm + SM_AUX + f32_off(jr, lane));
-                                    a4.x = fmaf(cf, z.x, a4.x), a4.y = fmaf(cf, z.y, a4.y);
-                                    a4.z = fmaf(cf, z.z, a4.z), a4.w = fmaf(cf, z.w, a4.w);
-                                    rs += cf;
+                        for (int n = 0; n < 4; ++n) {
+                            const int nb = c_nbr[j * 4 + n];
+                            if (nb < 0) break;
+                            const float cf = di * (1.0f / sqrtf((float)c_deg[nb]));
+                            rs += cf;
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) {
+                                const float4 z = *reinterpret_cast<const float4*>(sm + SM_AUX + f32_off(base + nb, e.half * 16 + c));
+                                xv[c * 4] = fmaf(cf, z.x, xv[c * 4]), xv[c * 4 + 1] = fmaf(cf, z.y, xv[c * 4 + 1]);
+                                xv[c * 4 + 2] = fmaf(cf, z.z, xv[c * 4 + 2]), xv[c * 4 + 3] = fmaf(cf, z.w, xv[c * 4 + 3]);
+                            }
+                        }
+                    } else {
+                        const uint32_t* adj = reinterpret_cast<const uint32_t*>(sm + SM_ADJ);
+                        const uint8_t* degs = sm + SM_DEG;
+                        const int gr0 = (e.row / p.T) * p.T;
+                        const float di = 1.0f / sqrtf((float)degs[e.row]);
+#pragma unroll 1
+                        for (int q = 0; q < 4; ++q) {
+                            unsigned bits = (32 * q < p.T) ? adj[e.row * 4 + q] : 0u;
+#pragma unroll 1
+                            while (bits) {
+                                const int jb = __ffs(bits) - 1;
+                                bits &= bits - 1;
+                                const int jr = gr0 + 32 * q + jb;
+                                const float cf = di * (1.0f / sqrtf((float)degs[jr]));
+                                rs += cf;
+#pragma unroll
+                                for (int c = 0; c < 16; ++c) {
+                                    const float4 z = *reinterpret_cast<const float4*>(sm + SM_AUX + f32_off(jr, e.half * 16 + c));
+                                    xv[c * 4] = fmaf(cf, z.x, xv[c * 4]), xv[c * 4 + 1] = fmaf(cf, z.y, xv[c * 4 + 1]);
+                                    xv[c * 4 + 2] = fmaf(cf, z.z, xv[c * 4 + 2]), xv[c * 4 + 3] = fmaf(cf, z.w, xv[c * 4 + 3]);
                                 }
                             }
                         }
                     }
-                    if (lane == 0) rowsum[r] = rs;
-                    uint2 pk;
-                    pk.x = pack_bf16(a4.x, a4.y);
-                    pk.y = pack_bf16(a4.z, a4.w);
-                    *reinterpret_cast<uint2*>(sm + SM_ATILE + tile_off_bf16(r, lane * 4)) = pk;
+                }
+                if (e.half == 0) *reinterpret_cast<float*>(sm + SM_ROWSUM + e.row * 4) = rs;
+                mma.wait();   // U z done: the A tile may be overwritten
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    uint4 pk;
+                    pk.x = pack_bf16(xv[c * 8 + 0], xv[c * 8 + 1]), pk.y = pack_bf16(xv[c * 8 + 2], xv[c * 8 + 3]);
+                    pk.z = pack_bf16(xv[c * 8 + 4], xv[c * 8 + 5]), pk.w = pack_bf16(xv[c * 8 + 6], xv[c * 8 + 7]);
+                    *reinterpret_cast<uint4*>(sm + SM_ATILE + tile_off_bf16(e.row, e.half * 64 + c * 8)) = pk;
                 }
                 fence_proxy_async();
                 tc_fence_before();
                 csync();
+                PMARK(7);
                 if (tid == 0) {
+                    tc_fence_after();
                     mma_chunk(TM_MIX, a_addr, true);    // += (A_hat z) V^T
                     tc_commit(&bars[B_MMA]);
                 }
                 mma.wait();
                 tc_fence_after();
+                PMARK(8);
             }
 
-            // ---- x1 = x + ls1 * mixer ; LN2 -> A operand
-            epilogue_mixer<KIND, MODE>(p, sm, vec, e, tile);
+            // ---- x1 = x + ls1 * mixer  (TMEM -> registers -> TMEM), LN2 -> A operand
+            {
+                // GCN: mix = relu(z + BN_node(acc + bU + rowsum*bV)); others: mix = acc + bproj
+                float bn_s = 1.f, bn_t = 0.f, rs = 0.f;
+                if (KIND == KASF_KIND_GRAPH) {
+                    const int node = MODE == KASF_MODE_SPATIAL ? e.row % J : e.row % p.T;
+                    bn_s = vec[V_BNS + node];
+                    bn_t = vec[V_BNT + node];
+                    rs = *reinterpret_cast<const float*>(sm + SM_ROWSUM + e.row * 4);
+                }
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    uint32_t acc[32], xr[32];
+                    tmem_ld32(e.tbase + TM_MIX + e.half * 64 + b * 32, acc);
+                    tmem_ld32(e.tbase + TM_X + e.half * 64 + b * 32, xr);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        const int col = e.half * 64 + b * 32 + c4 * 4;
+                        const float4 ls = *reinterpret_cast<const float4*>(vec + V_LS1 + col);
+                        const float4 bm = *reinterpret_cast<const float4*>(vec + V_BMIX + col);
+                        float m0 = __uint_as_float(acc[c4 * 4 + 0]) + bm.x, m1 = __uint_as_float(acc[c4 * 4 + 1]) + bm.y,
+                              m2 = __uint_as_float(acc[c4 * 4 + 2]) + bm.z, m3 = __uint_as_float(acc[c4 * 4 + 3]) + bm.w;
+                        if (KIND == KASF_KIND_GRAPH) {
+                            const float4 bv = *reinterpret_cast<const float4*>(vec + V_BV + col);
+                            const float4 z = *reinterpret_cast<const float4*>(sm + SM_AUX + f32_off(e.row, col >> 2));
+                            m0 = fmaxf(z.x + ((m0 + rs * bv.x) * bn_s + bn_t), 0.f);
+                            m1 = fmaxf(z.y + ((m1 + rs * bv.y) * bn_s + bn_t), 0.f);
+                            m2 = fmaxf(z.z + ((m2 + rs * bv.z) * bn_s + bn_t), 0.f);
+                            m3 = fmaxf(z.w + ((m3 + rs * bv.w) * bn_s + bn_t), 0.f);
+                        }
+                        xv[b * 32 + c4 * 4 + 0] = fmaf(ls.x, m0, __uint_as_float(xr[c4 * 4 + 0]));
+                        xv[b * 32 + c4 * 4 + 1] = fmaf(ls.y, m1, __uint_as_float(xr[c4 * 4 + 1]));
+                        xv[b * 32 + c4 * 4 + 2] = fmaf(ls.z, m2, __uint_as_float(xr[c4 * 4 + 2]));
+                        xv[b * 32 + c4 * 4 + 3] = fmaf(ls.w, m3, __uint_as_float(xr[c4 * 4 + 3]));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) xr[i] = __float_as_uint(xv[b * 32 + i]);
+                    tmem_st32(e.tbase + TM_X + e.half * 64 + b * 32, xr);
+                }
+            }
+            PMARK(9);
+            ln_stats(sm, e, xv, mean, rstd);
+            ln_write<false>(sm, e, xv, mean, rstd, vec + V_N2W, vec + V_N2B, row_ok);
+            tmem_st_wait();
+            fence_proxy_async();
             tc_fence_before();
             csync();
-            ln_tile<MODE, false, false, false>(p, sm, tile, nullptr, vec + V_N2W, vec + V_N2B, warp, lane);
-            fence_proxy_async();
-            csync();
+            PMARK(10);
 
             // ---- MLP: 4 hidden chunks of 128, software-pipelined over two TMEM / smem buffers
             if (tid == 0) {
@@ -690,37 +848,40 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
             }
             outb.wait();
             tc_fence_after();
-            // ---- out = x1 + ls2 * (acc + b2) -> STASH, then coalesced store
+            PMARK(11);
+            // ---- out = x1 + ls2 * (acc + b2) -> AUX (fp32, transposition buffer) -> coalesced row stores
 #pragma unroll
             for (int b = 0; b < 2; ++b) {
-                uint32_t acc[32];
+                uint32_t acc[32], xr[32];
                 tmem_ld32(e.tbase + TM_OUT + e.half * 64 + b * 32, acc);
+                tmem_ld32(e.tbase + TM_X + e.half * 64 + b * 32, xr);
                 tmem_ld_wait();
 #pragma unroll
                 for (int c4 = 0; c4 < 8; ++c4) {
                     const int col = e.half * 64 + b * 32 + c4 * 4;
-                    float4* xs = reinterpret_cast<float4*>(sm + SM_STASH + f32_off(e.row, col >> 2));
-                    float4 x = *xs;
                     const float4 ls = *reinterpret_cast<const float4*>(vec + V_LS2 + col);
                     const float4 b2 = *reinterpret_cast<const float4*>(vec + V_B2 + col);
-                    x.x = fmaf(ls.x, __uint_as_float(acc[c4 * 4 + 0]) + b2.x, x.x);
-                    x.y = fmaf(ls.y, __uint_as_float(acc[c4 * 4 + 1]) + b2.y, x.y);
-                    x.z = fmaf(ls.z, __uint_as_float(acc[c4 * 4 + 2]) + b2.z, x.z);
-                    x.w = fmaf(ls.w, __uint_as_float(acc[c4 * 4 + 3]) + b2.w, x.w);
-                    *xs = x;
+                    float4 x;
+                    x.x = fmaf(ls.x, __uint_as_float(acc[c4 * 4 + 0]) + b2.x, __uint_as_float(xr[c4 * 4 + 0]));
+                    x.y = fmaf(ls.y, __uint_as_float(acc[c4 * 4 + 1]) + b2.y, __uint_as_float(xr[c4 * 4 + 1]));
+                    x.z = fmaf(ls.z, __uint_as_float(acc[c4 * 4 + 2]) + b2.z, __uint_as_float(xr[c4 * 4 + 2]));
+                    x.w = fmaf(ls.w, __uint_as_float(acc[c4 * 4 + 3]) + b2.w, __uint_as_float(xr[c4 * 4 + 3]));
+                    *reinterpret_cast<float4*>(sm + SM_AUX + f32_off(e.row, col >> 2)) = x;
                 }
             }
             tc_fence_before();
             csync();
+            PMARK(12);
 #pragma unroll 4
             for (int rr = 0; rr < 16; ++rr) {
                 const int r = warp + CW * rr;
                 const long long tok = row_token<MODE>(p, tile, r);
                 if (tok >= 0)
                     *reinterpret_cast<float4*>(p.out + tok * D + lane * 4) =
-                        *reinterpret_cast<const float4*>(sm + SM_STASH + f32_off(r, lane));
+                        *reinterpret_cast<const float4*>(sm + SM_AUX + f32_off(r, lane));
             }
-            csync();   // STASH / AUX / ATILE are reused by the next tile
+            csync();   // AUX / ATILE are reused by the next tile
+            PMARK(13);
         }
     }
     tc_fence_before();
@@ -737,7 +898,7 @@ static int launch_one(const ModParams& p, cudaStream_t st) {
 }
 
 int launch_former_module(const uint8_t* blob, int layer, int kind, int mode, const float* in, const float* XL,
-                         float* out, int B, int T, cudaStream_t st) {
+                         float* out, int B, int T, cudaStream_t st, unsigned long long* prof) {
     if (B <= 0) return KASF_OK;
     if (kind < 0 || kind > 2 || mode < 0 || mode > 1) return KASF_EINVAL;
     if (kind == KASF_KIND_BONE && !XL) return KASF_EINVAL;
@@ -750,6 +911,7 @@ int launch_former_module(const uint8_t* blob, int layer, int kind, int mode, con
     p.out = out;
     p.B = B;
     p.T = T;
+    p.prof = prof;
     if (mode == KASF_MODE_SPATIAL) {
         p.groups_per_tile = 7;
         p.ntiles = (int)(((long long)B * T + 6) / 7);
