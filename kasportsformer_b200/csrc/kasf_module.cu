@@ -8,8 +8,11 @@
 // grouping.  A persistent CTA owns a tile of <=128 group-aligned tokens for the whole module: the fp32
 // residual rows are read from HBM once and written once; everything in between stays on chip.
 //
-//   residual rows ........... cp.async (LDGSTS) gather into smem, then resident in TENSOR MEMORY (128 of
-//                             the 512 TMEM columns) for the whole module; updated in place by the epilogues
+//   residual rows ........... each thread owns half a row (64 columns): 256-bit global loads issued ONE TILE
+//                             AHEAD into registers (the gather latency hides behind the previous tile's MLP),
+//                             then resident in TENSOR MEMORY (128 of the 512 TMEM columns) for the whole
+//                             module; updated in place by the epilogues; 256-bit stores straight from the
+//                             output epilogue (no staging, full 32-byte sectors)
 //   dense projections ....... tcgen05.mma (bf16 x bf16 -> fp32 in TMEM), operands in 128B-swizzled smem;
 //                             weights arrive pre-swizzled by bulk async copies (TMA engine) through a
 //                             3-slot mbarrier ring fed by a dedicated producer warp
@@ -21,7 +24,7 @@
 //                             ties, row-sum degrees, D^-1/2 A D^-1/2 applied as a sparse fp32 gather
 //   epilogues ............... thread per row straight out of TMEM (tcgen05.ld / tcgen05.st 32x32b)
 //
-// Shared memory map (bytes):   AUX    row staging / K|V bf16 / z fp32 / MLP hidden tiles   65536
+// Shared memory map (bytes):   AUX    K|V bf16 / z fp32 / MLP hidden tiles                 65536
 //                              ATILE  bf16 A operand [128 x 128] (also Q, attention output)  32768
 //                              RING   3 x weight chunk [128 x 128] bf16                      98304
 //                              VEC    the module's fp32 vectors (LN, layer scale, biases)     10240
@@ -34,6 +37,8 @@ namespace kasf {
 
 __constant__ int c_nbr[68] = KASF_NBR;
 __constant__ int c_deg[17] = KASF_DEG;
+// degree^-1/2 for the skeleton degrees 1..4 (index = degree)
+__constant__ float c_rsd[5] = {0.f, 1.0f, 0.70710678118654752440f, 0.57735026918962576451f, 0.5f};
 
 constexpr int CW = 8;                         // compute warps
 constexpr int MOD_THREADS = (CW + 4) * 32;    // + producer warpgroup (one working lane; register donor)
@@ -45,8 +50,8 @@ constexpr uint32_t SM_VEC = SM_RING + RING * 32768;   // 196608
 constexpr uint32_t SM_PART = SM_VEC + 10240;          // float2 [128][2]
 constexpr uint32_t SM_ADJ = SM_PART + 2048;           // u32 [128][4]
 constexpr uint32_t SM_ROWSUM = SM_ADJ + 2048;         // f32 [128]
-constexpr uint32_t SM_DEG = SM_ROWSUM + 512;          // u8  [128]
-constexpr uint32_t SM_BARS = SM_DEG + 128;
+constexpr uint32_t SM_RSD = SM_ROWSUM + 512;          // f32 [128]  degree^-1/2 of the temporal adjacency rows
+constexpr uint32_t SM_BARS = SM_RSD + 512;
 constexpr uint32_t SM_TOTAL = SM_BARS + 256;
 static_assert(SM_TOTAL <= 232448, "shared memory budget");
 static_assert(MOD_VEC_BYTES == 10240, "vector block size");
@@ -71,20 +76,20 @@ __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, 256;" ::: "m
 // the two warps (w, w+4) that share the rows of one TMEM lane quarter
 __device__ __forceinline__ void pair_sync(int warp) { asm volatile("bar.sync %0, 64;" ::"r"(2 + (warp & 3)) : "memory"); }
 
-// erf-GELU through tanh: 0.5 v (1 + erf(v / sqrt 2)) = 0.5 v (1 + tanh(v (a + b v^2 + c v^4))) with a minimax
-// fit of (a, b, c) (max abs deviation from the erf form 5.6e-5) and the hardware tanh (MUFU, rel. error
+// TWICE the erf-GELU, through tanh: v (1 + erf(v / sqrt 2)) = v (1 + tanh(v (a + b v^2 + c v^4))) with a minimax
+// fit of (a, b, c) (max abs deviation from the erf form 5.6e-5 on GELU) and the hardware tanh (MUFU, rel. error
 // 2^-11).  The result is rounded to bf16 (2^-9) right after, so this is below the operand rounding; the
-// exact erff form costs ~5x the instructions and made the MLP epilogue the bottleneck of the kernel.
-__device__ __forceinline__ float gelu_erf(float v) {
+// exact erff form costs ~5x the instructions and made the MLP epilogue the bottleneck of the kernel.  The
+// factor 1/2 lives in the packed fc2 weights (kasf_pack.cu), where it is exact.
+__device__ __forceinline__ float gelu2_erf(float v) {
 #ifdef KASF_EXACT_GELU
-    return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+    return v * (1.0f + erff(v * 0.70710678118654752440f));
 #else
     const float v2 = v * v;
     const float pl = fmaf(v2, fmaf(v2, -0.0003828259195935171f, 0.03722352208203997f), 0.7972238404651819f);
     float t;
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(v * pl));
-    const float hv = 0.5f * v;
-    return fmaf(hv, t, hv);
+    return fmaf(v, t, v);
 #endif
 }
 
@@ -118,20 +123,6 @@ __device__ __forceinline__ long long row_token(const ModParams& p, int tile, int
         const int j = (int)(seq % J), t = r - g * p.T;
         return (b * p.T + t) * J + j;
     }
-}
-
-// gather the 128 rows of a tile into AUX (fp32, swizzled): one 16-byte cp.async per lane and row, all 16
-// rows of a warp in flight at once; padding rows are zero-filled.
-template <int MODE>
-__device__ __forceinline__ void load_rows(const ModParams& p, uint8_t* sm, int tile, const float* src, int warp, int lane) {
-#pragma unroll 4
-    for (int rr = 0; rr < 16; ++rr) {
-        const int r = warp + CW * rr;
-        const long long tok = row_token<MODE>(p, tile, r);
-        const float* g = src + (tok >= 0 ? tok : 0) * D + lane * 4;
-        cp_async16(sm + SM_AUX + f32_off(r, lane), g, tok >= 0 ? 16u : 0u);
-    }
-    cp_async_commit();
 }
 
 // thread <-> (row, column half) mapping of everything that touches tensor memory
@@ -193,15 +184,6 @@ __device__ __forceinline__ void ln_write(uint8_t* sm, const EpiMap& e, const flo
             *reinterpret_cast<float4*>(sm + SM_AUX + f32_off(e.row, col >> 2)) = make_float4(z[0], z[1], z[2], z[3]);
             *reinterpret_cast<float4*>(sm + SM_AUX + f32_off(e.row, (col >> 2) + 1)) = make_float4(z[4], z[5], z[6], z[7]);
         }
-    }
-}
-
-// this thread's 64 staged values of its row
-__device__ __forceinline__ void read_staged(const uint8_t* sm, const EpiMap& e, float (&xv)[64]) {
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-        const float4 v = *reinterpret_cast<const float4*>(sm + SM_AUX + f32_off(e.row, e.half * 16 + c));
-        xv[c * 4] = v.x, xv[c * 4 + 1] = v.y, xv[c * 4 + 2] = v.z, xv[c * 4 + 3] = v.w;
     }
 }
 
@@ -341,7 +323,7 @@ __device__ __forceinline__ void attention_core_impl(uint8_t* sm, int warp, int l
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const float i0 = 1.0f / l0[u], i1 = 1.0f / l1[u];
+            const float i0 = rcp_approx(l0[u]), i1 = rcp_approx(l1[u]);
             const int qr0 = mt[u] * 16 + g8, qr1 = qr0 + 8;           // query index inside the group
 #pragma unroll
             for (int dn = 0; dn < 2; ++dn) {
@@ -372,7 +354,7 @@ __device__ __forceinline__ void attention_core(uint8_t* sm, int warp, int lane, 
 template <int MAXNT>
 __device__ __forceinline__ void similarity_topk_impl(uint8_t* sm, int warp, int lane, int T, int nrows) {
     uint32_t* adj = reinterpret_cast<uint32_t*>(sm + SM_ADJ);
-    uint8_t* degs = sm + SM_DEG;
+    float* rsd = reinterpret_cast<float*>(sm + SM_RSD);
     const int ngroups = nrows / T, mtiles = (T + 15) >> 4, nkt = (T + 7) >> 3;
     const int g8 = lane >> 2, t4 = lane & 3;
 #pragma unroll 1
@@ -462,7 +444,7 @@ __device__ __forceinline__ void similarity_topk_impl(uint8_t* sm, int warp, int 
                 deg += __popc(bits);
                 if (t4 == 0 && row < gr0 + T) adj[row * 4 + w] = bits;
             }
-            if (t4 == 0 && row < gr0 + T) degs[row] = (uint8_t)deg;
+            if (t4 == 0 && row < gr0 + T) rsd[row] = 1.0f / sqrtf((float)deg);
         }
     }
 }
@@ -516,7 +498,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
 #pragma unroll 1
                 for (int i = 0; i < NCH; ++i) {
                     const int ci = KIND == KASF_KIND_ATTENTION ? ORD_ATT[i] : (KIND == KASF_KIND_BONE ? ORD_BONE[i] : ORD_GCN[i]);
-                    while (!mbar_try_wait(&bars[B_EMPTY0 + slot], ph ^ 1)) __nanosleep(64);
+                    mbar_wait_suspend(&bars[B_EMPTY0 + slot], ph ^ 1);
                     mbar_arrive_expect_tx(&bars[B_FULL0 + slot], CHUNK_BYTES);
                     bulk_g2s(sm + SM_RING + slot * CHUNK_BYTES, chunks + (size_t)ci * CHUNK_BYTES, CHUNK_BYTES,
                              &bars[B_FULL0 + slot]);
@@ -558,6 +540,23 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
             pt0 = pt1;                                                \
         }                                                             \
     } while (0)
+        // this thread's 64 columns of its row, straight from global memory: eight 256-bit loads = eight full
+        // sectors.  Issued one tile ahead (at the start of the previous tile's MLP).
+        auto fetch_row = [&](const float* src, long long tok, float(&dst)[64]) {
+            if (tok >= 0) {
+                const float* g = src + tok * D + e.half * 64;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) ldg256(g + c * 8, dst + c * 8);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) dst[i] = 0.f;
+            }
+        };
+        const float* first_src = KIND == KASF_KIND_BONE ? p.xl : p.in;
+        float xn[64];
+        long long tok_next = (int)blockIdx.x < p.ntiles ? row_token<MODE>(p, blockIdx.x, e.row) : -1;
+        fetch_row(first_src, tok_next, xn);
+
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
             // rows of this tile that carry tokens, and the group geometry
             int gsize, nrows;
@@ -571,37 +570,31 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 nrows = (int)(left < p.groups_per_tile ? left : p.groups_per_tile) * p.T;
             }
             const bool row_ok = e.row < nrows;
+            const long long tok = tok_next;     // token of this thread's row (-1: padding row)
             float xv[64];
             float mean, rstd;
 
             if (KIND == KASF_KIND_BONE) {
-                // ---- K,V from the limb stream: LN_limb(XL) Wkv^T
-                load_rows<MODE>(p, sm, tile, p.xl, warp, lane);
-                cp_async_wait_all();
-                csync();
-                read_staged(sm, e, xv);
-                ln_stats(sm, e, xv, mean, rstd);
-                ln_write<false>(sm, e, xv, mean, rstd, vec + V_NLW, vec + V_NLB, row_ok);
+                // ---- K,V from the limb stream: LN_limb(XL) Wkv^T.  The residual rows of this tile are
+                //      requested first and land while LN_limb and the K,V MMAs run.
+                fetch_row(p.in, tok, xv);
+                ln_stats(sm, e, xn, mean, rstd);
+                ln_write<false>(sm, e, xn, mean, rstd, vec + V_NLW, vec + V_NLB, row_ok);
                 fence_proxy_async();
                 tc_fence_before();
-                csync();                                   // AUX is free again, the A tile is complete
+                csync();
                 if (tid == 0) {
                     tc_fence_after();
                     mma_chunk(TM_K, a_addr, false);
                     mma_chunk(TM_V, a_addr, false);
                     tc_commit(&bars[B_MMA]);
                 }
-                load_rows<MODE>(p, sm, tile, p.in, warp, lane);   // overlaps the K,V MMAs
-                mma.wait();                                // A tile free again (and K,V complete)
-                tc_fence_after();
                 PMARK(0);
             } else {
-                load_rows<MODE>(p, sm, tile, p.in, warp, lane);
+#pragma unroll
+                for (int i = 0; i < 64; ++i) xv[i] = xn[i];
             }
-            // ---- residual rows: smem staging -> registers -> tensor memory (resident); LN1 -> A operand
-            cp_async_wait_all();
-            csync();
-            read_staged(sm, e, xv);
+            // ---- residual rows: registers -> tensor memory (resident); LN1 -> A operand
 #pragma unroll
             for (int b = 0; b < 2; ++b) {
                 uint32_t xr[32];
@@ -610,6 +603,10 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 tmem_st32(e.tbase + TM_X + e.half * 64 + b * 32, xr);
             }
             ln_stats(sm, e, xv, mean, rstd);
+            if (KIND == KASF_KIND_BONE) {
+                mma.wait();                                // K,V complete: the A tile may be overwritten
+                tc_fence_after();
+            }
             ln_write<KIND == KASF_KIND_GRAPH>(sm, e, xv, mean, rstd, vec + V_N1W, vec + V_N1B, row_ok);
             tmem_st_wait();
             fence_proxy_async();
@@ -688,12 +685,12 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 if (row_ok) {
                     if (MODE == KASF_MODE_SPATIAL) {
                         const int j = e.row % J, base = e.row - j;
-                        const float di = 1.0f / sqrtf((float)c_deg[j]);
+                        const float di = c_rsd[c_deg[j]];
 #pragma unroll 1
                         for (int n = 0; n < 4; ++n) {
                             const int nb = c_nbr[j * 4 + n];
                             if (nb < 0) break;
-                            const float cf = di * (1.0f / sqrtf((float)c_deg[nb]));
+                            const float cf = di * c_rsd[c_deg[nb]];
                             rs += cf;
 #pragma unroll
                             for (int c = 0; c < 16; ++c) {
@@ -704,9 +701,9 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                         }
                     } else {
                         const uint32_t* adj = reinterpret_cast<const uint32_t*>(sm + SM_ADJ);
-                        const uint8_t* degs = sm + SM_DEG;
+                        const float* rsd = reinterpret_cast<const float*>(sm + SM_RSD);
                         const int gr0 = (e.row / p.T) * p.T;
-                        const float di = 1.0f / sqrtf((float)degs[e.row]);
+                        const float di = rsd[e.row];
 #pragma unroll 1
                         for (int q = 0; q < 4; ++q) {
                             unsigned bits = (32 * q < p.T) ? adj[e.row * 4 + q] : 0u;
@@ -715,7 +712,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                                 const int jb = __ffs(bits) - 1;
                                 bits &= bits - 1;
                                 const int jr = gr0 + 32 * q + jb;
-                                const float cf = di * (1.0f / sqrtf((float)degs[jr]));
+                                const float cf = di * rsd[jr];
                                 rs += cf;
 #pragma unroll
                                 for (int c = 0; c < 16; ++c) {
@@ -800,6 +797,12 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
             tc_fence_before();
             csync();
             PMARK(10);
+            // ---- request the next tile's rows now: they arrive while the MLP runs
+            {
+                const int ntile = tile + (int)gridDim.x;
+                tok_next = ntile < p.ntiles ? row_token<MODE>(p, ntile, e.row) : -1;
+                fetch_row(first_src, tok_next, xn);
+            }
 
             // ---- MLP: 4 hidden chunks of 128, software-pipelined over two TMEM / smem buffers
             if (tid == 0) {
@@ -829,10 +832,10 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                         const float4 ba = *reinterpret_cast<const float4*>(b1 + c8 * 8);
                         const float4 bb = *reinterpret_cast<const float4*>(b1 + c8 * 8 + 4);
                         uint4 pk;
-                        pk.x = pack_bf16(gelu_erf(__uint_as_float(acc[c8 * 8 + 0]) + ba.x), gelu_erf(__uint_as_float(acc[c8 * 8 + 1]) + ba.y));
-                        pk.y = pack_bf16(gelu_erf(__uint_as_float(acc[c8 * 8 + 2]) + ba.z), gelu_erf(__uint_as_float(acc[c8 * 8 + 3]) + ba.w));
-                        pk.z = pack_bf16(gelu_erf(__uint_as_float(acc[c8 * 8 + 4]) + bb.x), gelu_erf(__uint_as_float(acc[c8 * 8 + 5]) + bb.y));
-                        pk.w = pack_bf16(gelu_erf(__uint_as_float(acc[c8 * 8 + 6]) + bb.z), gelu_erf(__uint_as_float(acc[c8 * 8 + 7]) + bb.w));
+                        pk.x = pack_bf16(gelu2_erf(__uint_as_float(acc[c8 * 8 + 0]) + ba.x), gelu2_erf(__uint_as_float(acc[c8 * 8 + 1]) + ba.y));
+                        pk.y = pack_bf16(gelu2_erf(__uint_as_float(acc[c8 * 8 + 2]) + ba.z), gelu2_erf(__uint_as_float(acc[c8 * 8 + 3]) + ba.w));
+                        pk.z = pack_bf16(gelu2_erf(__uint_as_float(acc[c8 * 8 + 4]) + bb.x), gelu2_erf(__uint_as_float(acc[c8 * 8 + 5]) + bb.y));
+                        pk.w = pack_bf16(gelu2_erf(__uint_as_float(acc[c8 * 8 + 6]) + bb.z), gelu2_erf(__uint_as_float(acc[c8 * 8 + 7]) + bb.w));
                         *reinterpret_cast<uint4*>(sm + SM_AUX + buf * TILE_BYTES + tile_off_bf16(e.row, e.half * 64 + b * 32 + c8 * 8)) = pk;
                     }
                 }
@@ -849,39 +852,36 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
             outb.wait();
             tc_fence_after();
             PMARK(11);
-            // ---- out = x1 + ls2 * (acc + b2) -> AUX (fp32, transposition buffer) -> coalesced row stores
+            // ---- out = x1 + ls2 * (acc + b2): 256-bit stores of this thread's 64 columns, straight from registers
+            {
+                float* orow = p.out + (tok >= 0 ? tok : 0) * D + e.half * 64;
 #pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                uint32_t acc[32], xr[32];
-                tmem_ld32(e.tbase + TM_OUT + e.half * 64 + b * 32, acc);
-                tmem_ld32(e.tbase + TM_X + e.half * 64 + b * 32, xr);
-                tmem_ld_wait();
+                for (int b = 0; b < 2; ++b) {
+                    uint32_t acc[32], xr[32];
+                    tmem_ld32(e.tbase + TM_OUT + e.half * 64 + b * 32, acc);
+                    tmem_ld32(e.tbase + TM_X + e.half * 64 + b * 32, xr);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    const int col = e.half * 64 + b * 32 + c4 * 4;
-                    const float4 ls = *reinterpret_cast<const float4*>(vec + V_LS2 + col);
-                    const float4 b2 = *reinterpret_cast<const float4*>(vec + V_B2 + col);
-                    float4 x;
-                    x.x = fmaf(ls.x, __uint_as_float(acc[c4 * 4 + 0]) + b2.x, __uint_as_float(xr[c4 * 4 + 0]));
-                    x.y = fmaf(ls.y, __uint_as_float(acc[c4 * 4 + 1]) + b2.y, __uint_as_float(xr[c4 * 4 + 1]));
-                    x.z = fmaf(ls.z, __uint_as_float(acc[c4 * 4 + 2]) + b2.z, __uint_as_float(xr[c4 * 4 + 2]));
-                    x.w = fmaf(ls.w, __uint_as_float(acc[c4 * 4 + 3]) + b2.w, __uint_as_float(xr[c4 * 4 + 3]));
-                    *reinterpret_cast<float4*>(sm + SM_AUX + f32_off(e.row, col >> 2)) = x;
+                    for (int c8 = 0; c8 < 4; ++c8) {
+                        const int col = e.half * 64 + b * 32 + c8 * 8;
+                        float o[8];
+#pragma unroll
+                        for (int h4 = 0; h4 < 2; ++h4) {
+                            const float4 ls = *reinterpret_cast<const float4*>(vec + V_LS2 + col + h4 * 4);
+                            const float4 b2 = *reinterpret_cast<const float4*>(vec + V_B2 + col + h4 * 4);
+                            const int i = c8 * 8 + h4 * 4;
+                            o[h4 * 4 + 0] = fmaf(ls.x, __uint_as_float(acc[i + 0]) + b2.x, __uint_as_float(xr[i + 0]));
+                            o[h4 * 4 + 1] = fmaf(ls.y, __uint_as_float(acc[i + 1]) + b2.y, __uint_as_float(xr[i + 1]));
+                            o[h4 * 4 + 2] = fmaf(ls.z, __uint_as_float(acc[i + 2]) + b2.z, __uint_as_float(xr[i + 2]));
+                            o[h4 * 4 + 3] = fmaf(ls.w, __uint_as_float(acc[i + 3]) + b2.w, __uint_as_float(xr[i + 3]));
+                        }
+                        if (tok >= 0) stg256(orow + b * 32 + c8 * 8, o);
+                    }
                 }
             }
-            tc_fence_before();
-            csync();
+            // (no CTA barrier here: the next tile's first shared-memory writes touch buffers whose last readers
+            //  were MMAs already observed complete by every thread, and its first MMA follows a csync)
             PMARK(12);
-#pragma unroll 4
-            for (int rr = 0; rr < 16; ++rr) {
-                const int r = warp + CW * rr;
-                const long long tok = row_token<MODE>(p, tile, r);
-                if (tok >= 0)
-                    *reinterpret_cast<float4*>(p.out + tok * D + lane * 4) =
-                        *reinterpret_cast<const float4*>(sm + SM_AUX + f32_off(r, lane));
-            }
-            csync();   // AUX / ATILE are reused by the next tile
-            PMARK(13);
         }
     }
     tc_fence_before();
@@ -903,6 +903,7 @@ int launch_former_module(const uint8_t* blob, int layer, int kind, int mode, con
     if (kind < 0 || kind > 2 || mode < 0 || mode > 1) return KASF_EINVAL;
     if (kind == KASF_KIND_BONE && !XL) return KASF_EINVAL;
     if (mode == KASF_MODE_TEMPORAL && T > 128) return KASF_ESHAPE;   // TODO: two-tile sequences (T=243)
+    if ((((uintptr_t)in | (uintptr_t)out | (uintptr_t)XL) & 31) != 0) return KASF_EINVAL;   // 256-bit row accesses
     ModParams p;
     // module order in the blob: att_s, att_t, graph_s, graph_t, bone_s, bone_t
     p.mod = blob + module_off(layer, kind * 2 + mode);

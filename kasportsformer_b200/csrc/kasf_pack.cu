@@ -45,6 +45,7 @@ __global__ void pack_chunks_kernel(const float* __restrict__ img, uint8_t* __res
             v0 = src[(size_t)n * ld + k];
             v1 = src[(size_t)n * ld + k + 1];
         }
+        if (c >= 8) v0 *= 0.5f, v1 *= 0.5f;   // the MLP epilogue produces 2*GELU (exact power-of-two rescaling)
         *reinterpret_cast<uint32_t*>(dst + tile_off_bf16(n, k)) = pack_bf16(v0, v1);
     }
 }

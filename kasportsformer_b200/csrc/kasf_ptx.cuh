@@ -40,6 +40,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// same, but the thread is suspended by the hardware between polls (producer side: long waits, no issue slots)
+__device__ __forceinline__ void mbar_wait_suspend(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "KASF_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra KASF_DONE_%=;\n\t"
+        "bra KASF_WAIT_%=;\n\t"
+        "KASF_DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(0x989680u)
+        : "memory");
+}
 
 // generic-proxy writes to shared memory -> visible to the async proxy (UMMA / bulk copies)
 __device__ __forceinline__ void fence_proxy_async() {
@@ -54,6 +66,24 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
             smem_u32(smem_dst)),
         "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
+}
+
+// ---------------------------------------------------------------- 256-bit global accesses (LDG/STG.E.256)
+// one full 32-byte sector per thread and instruction; addresses must be 32-byte aligned
+__device__ __forceinline__ void ldg256(const float* p, float* v) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                 "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 // ---------------------------------------------------------------- tcgen05 / TMEM
