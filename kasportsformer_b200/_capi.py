@@ -14,7 +14,8 @@ from typing import Dict, Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkasf.so")
+# KASF_LIB selects another build of the same library (A/B measurements of kernel variants); never a fallback
+LIB_PATH = os.environ.get("KASF_LIB") or os.path.join(_HERE, "libkasf.so")
 
 KIND = {"attention": 0, "graph": 1, "bone": 2}
 MODE = {"spatial": 0, "temporal": 1}
@@ -264,7 +265,7 @@ def former_module(cfg, blob, layer, kind, mode, v, XL=None, out=None):
 
 
 PHASES = ["limb_kv", "load_ln1", "qkv_mma_wait", "qkv_drain", "attention", "proj_mma_wait", "similarity",
-          "aggregation", "v_mma_wait", "mixer_epilogue", "ln2", "mlp", "out_epilogue", "store"]
+          "aggregation", "v_mma_wait", "mixer_epilogue", "ln2", "mlp", "out_epilogue", "rows_wait"]
 
 
 def former_module_phases(cfg, blob, layer, kind, mode, v, XL=None):

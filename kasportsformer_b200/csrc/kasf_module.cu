@@ -40,13 +40,16 @@ __constant__ int c_deg[17] = KASF_DEG;
 // degree^-1/2 for the skeleton degrees 1..4 (index = degree)
 __constant__ float c_rsd[5] = {0.f, 1.0f, 0.70710678118654752440f, 0.57735026918962576451f, 0.5f};
 
-constexpr int CW = 8;                         // compute warps
-constexpr int MOD_THREADS = (CW + 4) * 32;    // + producer warpgroup (one working lane; register donor)
+constexpr int CW = 8;                         // compute warps (TMEM epilogues, LayerNorm, mixer cores)
+constexpr int MOD_THREADS = (CW + 4) * 32;    // + service warpgroup: weight producer, MMA issuer, row gatherer
+constexpr int W_PRODUCER = CW, W_MMA = CW + 1, W_GATHER = CW + 2;
 constexpr int RING = 3;
+constexpr uint32_t ROW_PITCH = 528;                   // staged fp32 row: 512 B + 16 B pad (conflict-free thread-per-row reads)
 constexpr uint32_t SM_AUX = 0;
-constexpr uint32_t SM_ATILE = 65536;
-constexpr uint32_t SM_RING = 98304;
-constexpr uint32_t SM_VEC = SM_RING + RING * 32768;   // 196608
+constexpr uint32_t AUX_BYTES = 128 * ROW_PITCH;       // 67584 (a multiple of 1024)
+constexpr uint32_t SM_ATILE = SM_AUX + AUX_BYTES;
+constexpr uint32_t SM_RING = SM_ATILE + 32768;
+constexpr uint32_t SM_VEC = SM_RING + RING * 32768;
 constexpr uint32_t SM_PART = SM_VEC + 10240;          // float2 [128][2]
 constexpr uint32_t SM_ADJ = SM_PART + 2048;           // u32 [128][4]
 constexpr uint32_t SM_ROWSUM = SM_ADJ + 2048;         // f32 [128]
@@ -55,11 +58,19 @@ constexpr uint32_t SM_BARS = SM_RSD + 512;
 constexpr uint32_t SM_TOTAL = SM_BARS + 256;
 static_assert(SM_TOTAL <= 232448, "shared memory budget");
 static_assert(MOD_VEC_BYTES == 10240, "vector block size");
+static_assert(AUX_BYTES % 1024 == 0 && AUX_BYTES >= 65536, "operand tiles behind AUX must stay 1024-byte aligned");
 
 constexpr uint32_t TM_MIX = 0, TM_K = 128, TM_V = 256, TM_X = 384;   // mixer phase (Q lives at TM_MIX)
 constexpr uint32_t TM_H0 = 0, TM_H1 = 128, TM_OUT = 256;            // MLP phase
 
-enum { B_FULL0 = 0, B_EMPTY0 = RING, B_MMA = 2 * RING, B_HFULL0, B_HFULL1, B_HSFREE0, B_HSFREE1, B_OUT, B_COUNT };
+// mbarriers.  Ring: FULL (bulk-copy bytes) / EMPTY (tcgen05.commit).  Compute warps -> MMA warp: AREADY (the A
+// operand tile is written), HSREADY (hidden tile c written, hidden accumulator drained).  MMA warp -> compute
+// warps: MMA (mixer projections done), HFULL (fc1 chunk in TMEM), HSFREE (fc2 has read the hidden tile),
+// OUT (fc2 complete).  Gather warp <-> compute warps: ROWS (staged rows landed), TAKEN (staged rows consumed).
+// Gather warp -> weight producer: GO (the first rows of the tile have landed: weights may use the L2 port now).
+enum { B_FULL0 = 0, B_EMPTY0 = RING, B_AREADY = 2 * RING, B_MMA, B_HFULL0, B_HFULL1, B_HSREADY0, B_HSREADY1,
+       B_HSFREE0, B_HSFREE1, B_OUT, B_ROWS, B_TAKEN, B_GO, B_COUNT };
+static_assert(B_COUNT * 8 + 8 <= 256, "barrier block");
 
 struct ModParams {
     const uint8_t* mod;      // packed module (vector block + chunks)
@@ -81,15 +92,22 @@ __device__ __forceinline__ void pair_sync(int warp) { asm volatile("bar.sync %0,
 // 2^-11).  The result is rounded to bf16 (2^-9) right after, so this is below the operand rounding; the
 // exact erff form costs ~5x the instructions and made the MLP epilogue the bottleneck of the kernel.  The
 // factor 1/2 lives in the packed fc2 weights (kasf_pack.cu), where it is exact.
-__device__ __forceinline__ float gelu2_erf(float v) {
+// 2*GELU(v) = fma(v, gelu2_tanh(gelu2_arg(v)), v): split so that the epilogue can software-pipeline the MUFU
+__device__ __forceinline__ float gelu2_arg(float v) {
 #ifdef KASF_EXACT_GELU
-    return v * (1.0f + erff(v * 0.70710678118654752440f));
+    return v;
 #else
     const float v2 = v * v;
-    const float pl = fmaf(v2, fmaf(v2, -0.0003828259195935171f, 0.03722352208203997f), 0.7972238404651819f);
+    return v * fmaf(v2, fmaf(v2, -0.0003828259195935171f, 0.03722352208203997f), 0.7972238404651819f);
+#endif
+}
+__device__ __forceinline__ float gelu2_tanh(float w) {
+#ifdef KASF_EXACT_GELU
+    return erff(w * 0.70710678118654752440f);
+#else
     float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(v * pl));
-    return fmaf(v, t, v);
+    asm volatile("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(w));
+    return t;
 #endif
 }
 
@@ -217,13 +235,15 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // 17x17 / TxT with head_dim 16 -- far too small and too many for tcgen05 tiles.  Q [128 x 128] bf16 sits in
 // the A tile (operand layout), K|V in AUX.  A work item is (group, head, 16-query block); its output
 // overwrites the Q block it consumed.  U independent items are interleaved per warp to hide the
-// ldmatrix -> mma -> shuffle -> ex2 -> mma dependency chain.
-template <int MAXNT, int U>   // MAXNT: key tiles of 8 held in registers (gsize <= 8 * MAXNT)
-__device__ __forceinline__ void attention_core_impl(uint8_t* sm, int warp, int lane, int gsize, int nrows) {
+// ldmatrix -> mma -> shuffle -> ex2 -> mma dependency chain.  GS > 0: the group size is a compile-time
+// constant (17 joints), so key tiles past the group and the key masks fold away.
+template <int MAXNT, int U, int GS>   // MAXNT: key tiles of 8 held in registers (gsize <= 8 * MAXNT)
+__device__ __forceinline__ void attention_core_impl(uint8_t* sm, int warp, int lane, int gsize_rt, int nrows) {
     const uint32_t q_base = smem_u32(sm + SM_ATILE), kv_base = smem_u32(sm + SM_AUX);
+    const int gsize = GS ? GS : gsize_rt;
     const int ngroups = nrows / gsize;
     const int mtiles = (gsize + 15) >> 4;
-    const int nkt = ((gsize + 15) >> 4) << 1;                     // key tiles, rounded up to pairs
+    const int nkt = (gsize + 7) >> 3;                             // key tiles that hold keys of the group
     const int items = ngroups * HEADS * mtiles;
     const int g8 = lane >> 2, t4 = lane & 3, mi = lane >> 3, r8 = lane & 7;
     const float scale = 0.25f * 1.4426950408889634f;              // head_dim^-1/2 * log2(e)
@@ -237,8 +257,9 @@ __device__ __forceinline__ void attention_core_impl(uint8_t* sm, int warp, int l
         for (int u = 0; u < U; ++u) {
             live[u] = it0 + u < items;
             const int item = live[u] ? it0 + u : it0;
-            mt[u] = item % mtiles, h[u] = (item / mtiles) % HEADS;
-            gr0[u] = (item / (mtiles * HEADS)) * gsize;
+            const int gh = item / mtiles;
+            mt[u] = item - gh * mtiles, h[u] = gh & (HEADS - 1);
+            gr0[u] = (gh >> 3) * gsize;
             const int row = min(gr0[u] + mt[u] * 16 + (mi & 1) * 8 + r8, 127);
             ldsm_x4(q_base + tile_off_bf16(row, h[u] * DH + (mi >> 1) * 8), qa[u]);
         }
@@ -253,11 +274,12 @@ __device__ __forceinline__ void attention_core_impl(uint8_t* sm, int warp, int l
 #pragma unroll
                     for (int i = 0; i < 4; ++i) s[u][nt][i] = 0.f, s[u][nt + 1][i] = 0.f;
                     mma_bf16_16816(s[u][nt], qa[u], kb[0], kb[1]);
-                    mma_bf16_16816(s[u][nt + 1], qa[u], kb[2], kb[3]);
+                    if (nt + 1 < nkt) mma_bf16_16816(s[u][nt + 1], qa[u], kb[2], kb[3]);
                 }
             }
         }
-        // ---- softmax over the keys of the group (rows g8 and g8+8 of the block), fp32
+        // ---- softmax over the keys of the group (rows g8 and g8+8 of the block), fp32; the 1/4 * log2(e)
+        //      scale rides in the FFMA that feeds ex2
         float l0[U], l1[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -268,7 +290,7 @@ __device__ __forceinline__ void attention_core_impl(uint8_t* sm, int warp, int l
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int key = nt * 8 + t4 * 2 + (i & 1);
-                        s[u][nt][i] = key < gsize ? s[u][nt][i] * scale : -INFINITY;
+                        if (!(key < gsize)) s[u][nt][i] = -INFINITY;
                     }
                     mx0 = fmaxf(mx0, fmaxf(s[u][nt][0], s[u][nt][1]));
                     mx1 = fmaxf(mx1, fmaxf(s[u][nt][2], s[u][nt][3]));
@@ -278,14 +300,15 @@ __device__ __forceinline__ void attention_core_impl(uint8_t* sm, int warp, int l
             mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
             mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
             mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+            const float nm0 = -mx0 * scale, nm1 = -mx1 * scale;
             float a0 = 0.f, a1 = 0.f;
 #pragma unroll
             for (int nt = 0; nt < MAXNT; ++nt) {
                 if (nt < nkt) {
-                    s[u][nt][0] = ex2_approx(s[u][nt][0] - mx0);
-                    s[u][nt][1] = ex2_approx(s[u][nt][1] - mx0);
-                    s[u][nt][2] = ex2_approx(s[u][nt][2] - mx1);
-                    s[u][nt][3] = ex2_approx(s[u][nt][3] - mx1);
+                    s[u][nt][0] = ex2_approx(fmaf(s[u][nt][0], scale, nm0));
+                    s[u][nt][1] = ex2_approx(fmaf(s[u][nt][1], scale, nm0));
+                    s[u][nt][2] = ex2_approx(fmaf(s[u][nt][2], scale, nm1));
+                    s[u][nt][3] = ex2_approx(fmaf(s[u][nt][3], scale, nm1));
                     a0 += s[u][nt][0] + s[u][nt][1];
                     a1 += s[u][nt][2] + s[u][nt][3];
                 }
@@ -312,8 +335,12 @@ __device__ __forceinline__ void attention_core_impl(uint8_t* sm, int warp, int l
                     uint32_t pa[4], vb[4];
                     pa[0] = pack_bf16(s[u][2 * ks][0], s[u][2 * ks][1]);
                     pa[1] = pack_bf16(s[u][2 * ks][2], s[u][2 * ks][3]);
-                    pa[2] = pack_bf16(s[u][2 * ks + 1][0], s[u][2 * ks + 1][1]);
-                    pa[3] = pack_bf16(s[u][2 * ks + 1][2], s[u][2 * ks + 1][3]);
+                    if (2 * ks + 1 < nkt) {
+                        pa[2] = pack_bf16(s[u][2 * ks + 1][0], s[u][2 * ks + 1][1]);
+                        pa[3] = pack_bf16(s[u][2 * ks + 1][2], s[u][2 * ks + 1][3]);
+                    } else {
+                        pa[2] = 0u, pa[3] = 0u;
+                    }
                     const int row = min(gr0[u] + 16 * ks + (mi & 1) * 8 + r8, 127);
                     ldsm_x4_t(kv_base + f32_off(row, 16 + 2 * h[u] + (mi >> 1)), vb);
                     mma_bf16_16816(o[u][0], pa, vb[0], vb[1]);
@@ -325,25 +352,28 @@ __device__ __forceinline__ void attention_core_impl(uint8_t* sm, int warp, int l
         for (int u = 0; u < U; ++u) {
             const float i0 = rcp_approx(l0[u]), i1 = rcp_approx(l1[u]);
             const int qr0 = mt[u] * 16 + g8, qr1 = qr0 + 8;           // query index inside the group
+            const uint32_t o0 = tile_off_bf16(gr0[u] + qr0, h[u] * DH + t4 * 2), o1 = tile_off_bf16(gr0[u] + qr1, h[u] * DH + t4 * 2);
 #pragma unroll
             for (int dn = 0; dn < 2; ++dn) {
-                const int col = h[u] * DH + dn * 8 + t4 * 2;
+                // columns h*16 + dn*8 + ..: the next 16-byte chunk of the row, i.e. chunk index ^ 1 after swizzling
+                const uint32_t x0 = dn ? (o0 ^ 16u) : o0, x1 = dn ? (o1 ^ 16u) : o1;
                 if (live[u] && qr0 < gsize)
-                    *reinterpret_cast<uint32_t*>(sm + SM_ATILE + tile_off_bf16(gr0[u] + qr0, col)) =
-                        pack_bf16(o[u][dn][0] * i0, o[u][dn][1] * i0);
+                    *reinterpret_cast<uint32_t*>(sm + SM_ATILE + x0) = pack_bf16(o[u][dn][0] * i0, o[u][dn][1] * i0);
                 if (live[u] && qr1 < gsize)
-                    *reinterpret_cast<uint32_t*>(sm + SM_ATILE + tile_off_bf16(gr0[u] + qr1, col)) =
-                        pack_bf16(o[u][dn][2] * i1, o[u][dn][3] * i1);
+                    *reinterpret_cast<uint32_t*>(sm + SM_ATILE + x1) = pack_bf16(o[u][dn][2] * i1, o[u][dn][3] * i1);
             }
         }
     }
 }
 
-template <int MODE>
+// TC = sequence-length class of the instantiation: 0: group size <= 32, 1: <= 64, 2: <= 128 (key tiles held in
+// registers).  One class per kernel keeps the cold variants out of the register allocation.
+template <int MODE, int TC>
 __device__ __forceinline__ void attention_core(uint8_t* sm, int warp, int lane, int gsize, int nrows) {
-    if (MODE == KASF_MODE_SPATIAL || gsize <= 32) attention_core_impl<4, 2>(sm, warp, lane, gsize, nrows);
-    else if (gsize <= 64) attention_core_impl<8, 1>(sm, warp, lane, gsize, nrows);
-    else attention_core_impl<16, 1>(sm, warp, lane, gsize, nrows);
+    if (MODE == KASF_MODE_SPATIAL) attention_core_impl<4, 4, J>(sm, warp, lane, gsize, nrows);
+    else if (TC == 0) attention_core_impl<4, 4, 0>(sm, warp, lane, gsize, nrows);
+    else if (TC == 1) attention_core_impl<8, 2, 0>(sm, warp, lane, gsize, nrows);
+    else attention_core_impl<16, 1, 0>(sm, warp, lane, gsize, nrows);
 }
 
 // ---------------------------------------------------------------------------------------------- temporal adjacency
@@ -449,14 +479,84 @@ __device__ __forceinline__ void similarity_topk_impl(uint8_t* sm, int warp, int 
     }
 }
 
+template <int TC>
 __device__ __forceinline__ void similarity_topk(uint8_t* sm, int warp, int lane, int T, int nrows) {
-    if (T <= 32) similarity_topk_impl<4>(sm, warp, lane, T, nrows);
-    else if (T <= 64) similarity_topk_impl<8>(sm, warp, lane, T, nrows);
-    else similarity_topk_impl<16>(sm, warp, lane, T, nrows);
+    similarity_topk_impl<TC == 0 ? 4 : (TC == 1 ? 8 : 16)>(sm, warp, lane, T, nrows);
+}
+
+// ---------------------------------------------------------------------------------------------- tile geometry
+// rows of tile `tile` that carry tokens (rows [0, n) are valid, the rest is padding)
+template <int MODE>
+__device__ __forceinline__ int tile_rows(const ModParams& p, int tile) {
+    if (MODE == KASF_MODE_SPATIAL) {
+        const long long left = (long long)p.B * p.T * J - (long long)tile * 119;
+        return (int)(left < 119 ? left : 119);
+    } else {
+        const long long left = (long long)p.B * J - (long long)tile * p.groups_per_tile;
+        return (int)(left < p.groups_per_tile ? left : p.groups_per_tile) * p.T;
+    }
+}
+
+// Row gather of one tile by the gather warp: one coalesced 512-byte cp.async (LDGSTS, 16 B per lane) per row into
+// the padded staging rows of AUX; every lane then attaches the completion of its copies to `bar` (32 arrivals).
+// No registers hold data and the latency is off the compute warps' critical path.
+template <int MODE>
+__device__ __forceinline__ void gather_rows(const ModParams& p, uint8_t* sm, int tile, const float* src, uint64_t* bar,
+                                            uint64_t* bar2, int lane) {
+    const int n = tile_rows<MODE>(p, tile);
+    uint8_t* dst = sm + SM_AUX + lane * 16;
+    if (MODE == KASF_MODE_SPATIAL) {
+        const float* g = src + (long long)tile * 119 * D + lane * 4;
+#pragma unroll 4
+        for (int r = 0; r < n; ++r) cp_async16(dst + r * ROW_PITCH, g + (size_t)r * D, 16u);
+    } else {
+        // lane l knows the tokens of rows l, l+32, l+64, l+96; they are broadcast row by row
+        int mytok[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mytok[k] = lane + 32 * k < n ? (int)row_token<MODE>(p, tile, lane + 32 * k) : 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int cnt = min(32, n - 32 * k);
+#pragma unroll 4
+            for (int l = 0; l < cnt; ++l) {
+                const int tok = __shfl_sync(0xffffffffu, mytok[k], l);
+                cp_async16(dst + (32 * k + l) * ROW_PITCH, src + (size_t)tok * D + lane * 4, 16u);
+            }
+        }
+    }
+    cp_async_mbar_arrive(bar);
+    if (bar2) cp_async_mbar_arrive(bar2);
+}
+
+// this thread's 64 staged values of its row (zeros for padding rows)
+__device__ __forceinline__ void read_staged(const uint8_t* sm, const EpiMap& e, float (&xv)[64], bool ok) {
+    if (ok) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const float4 v = *reinterpret_cast<const float4*>(sm + SM_AUX + e.row * ROW_PITCH + (e.half * 16 + c) * 16);
+            xv[c * 4] = v.x, xv[c * 4 + 1] = v.y, xv[c * 4 + 2] = v.z, xv[c * 4 + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) xv[i] = 0.f;
+    }
+}
+
+// compute warp -> MMA warp: this warp's part of a shared-memory operand tile is written (generic proxy) and
+// its tensor-memory reads are complete
+__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+    fence_proxy_async();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
 }
 
 // ----------------------------------------------------------------------------------------------
-template <int KIND, int MODE>
+// Warp roles: 8 compute warps | weight producer (1 lane) | MMA issuer (1 lane) | row gatherer (1 warp).
+// The compute warps never issue an MMA and (apart from the mixer cores, which exchange rows through shared
+// memory) never meet at a CTA barrier: every hand-over is an mbarrier, so warps drift apart and the MUFU-bound
+// GELU epilogues of one warp overlap the tensor-memory loads, stores and MMAs triggered by the others.
+template <int KIND, int MODE, int TC>
 __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const ModParams p) {
     extern __shared__ __align__(1024) uint8_t sm[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM_BARS);
@@ -467,7 +567,10 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
 
     if (tid == 0) {
         if ((smem_u32(sm) & 1023u) != 0) __trap();
-        for (int i = 0; i < B_COUNT; ++i) mbar_init(&bars[i], 1);
+        for (int i = 0; i < B_COUNT; ++i) {
+            const bool by_warps = i == B_AREADY || i == B_HSREADY0 || i == B_HSREADY1 || i == B_TAKEN;
+            mbar_init(&bars[i], by_warps ? CW : (i == B_ROWS || i == B_GO ? 32 : 1));
+        }
         fence_mbar_init();
     }
     if (warp == 0) {
@@ -483,26 +586,113 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
 
     // chunk consumption order (indices into the module's 12 chunks; see kasf_layout.h)
     constexpr int NCH = KIND == KASF_KIND_GRAPH ? 10 : 12;
-    //                         mixer chunks                         MLP: W1_0 W1_1 W2_0 W1_2 W2_1 W1_3 W2_2 W2_3
-    constexpr int ORD_ATT[12] = {0, 1, 2, 3, 4, 5, 8, 6, 9, 7, 10, 11};
-    constexpr int ORD_BONE[12] = {1, 2, 0, 3, 4, 5, 8, 6, 9, 7, 10, 11};
-    constexpr int ORD_GCN[12] = {0, 1, 4, 5, 8, 6, 9, 7, 10, 11, 0, 0};
+    //                         mixer chunks                         MLP: W1_0 W1_1 W1_2 W2_0 W1_3 W2_1 W2_2 W2_3
+    constexpr int ORD_ATT[12] = {0, 1, 2, 3, 4, 5, 6, 8, 7, 9, 10, 11};
+    constexpr int ORD_BONE[12] = {1, 2, 0, 3, 4, 5, 6, 8, 7, 9, 10, 11};
+    constexpr int ORD_GCN[12] = {0, 1, 4, 5, 6, 8, 7, 9, 10, 11, 0, 0};
+    const float* first_src = KIND == KASF_KIND_BONE ? p.xl : p.in;
 
     if (warp >= CW) {
-        // ===================== producer warpgroup: stream weight chunks through the ring =====================
-        // (hands its registers to the compute warpgroups: 8 x 232 + 4 x 40 regs per thread fit the file)
+        // ===================== service warpgroup (hands its registers to the compute warpgroups) =====================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        if (warp == CW && lane == 0) {
-            uint32_t slot = 0, ph = 0;
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        if (warp == W_PRODUCER) {
+            // ---- weight chunks: L2 -> ring slots (bulk copies, MMA-ready swizzled images)
+            if (lane == 0) {
+                // The SM's L2 port (~40 B/clk when every SM streams) is the scarce resource at a tile boundary: the
+                // 60 KB of rows the next LayerNorm waits for go first, the 96 KB of ring refills after them.
+                uint32_t slot = 0, ph = 0, ph_go = 0;
+                for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                    mbar_wait_suspend(&bars[B_GO], ph_go);
+                    ph_go ^= 1;
 #pragma unroll 1
-                for (int i = 0; i < NCH; ++i) {
-                    const int ci = KIND == KASF_KIND_ATTENTION ? ORD_ATT[i] : (KIND == KASF_KIND_BONE ? ORD_BONE[i] : ORD_GCN[i]);
-                    mbar_wait_suspend(&bars[B_EMPTY0 + slot], ph ^ 1);
-                    mbar_arrive_expect_tx(&bars[B_FULL0 + slot], CHUNK_BYTES);
-                    bulk_g2s(sm + SM_RING + slot * CHUNK_BYTES, chunks + (size_t)ci * CHUNK_BYTES, CHUNK_BYTES,
-                             &bars[B_FULL0 + slot]);
-                    if (++slot == RING) slot = 0, ph ^= 1;
+                    for (int i = 0; i < NCH; ++i) {
+                        const int ci = KIND == KASF_KIND_ATTENTION ? ORD_ATT[i] : (KIND == KASF_KIND_BONE ? ORD_BONE[i] : ORD_GCN[i]);
+                        mbar_wait_suspend(&bars[B_EMPTY0 + slot], ph ^ 1);
+                        mbar_arrive_expect_tx(&bars[B_FULL0 + slot], CHUNK_BYTES);
+                        bulk_g2s(sm + SM_RING + slot * CHUNK_BYTES, chunks + (size_t)ci * CHUNK_BYTES, CHUNK_BYTES,
+                                 &bars[B_FULL0 + slot]);
+                        if (++slot == RING) slot = 0, ph ^= 1;
+                    }
+                }
+            }
+        } else if (warp == W_GATHER) {
+            // ---- residual (and limb) rows of the NEXT tile -> AUX as soon as fc2 of the current tile has
+            //      finished reading its hidden tiles: the gather overlaps the output epilogue
+            uint32_t ph_out = 0, ph_taken = 0;
+            if ((int)blockIdx.x < p.ntiles) gather_rows<MODE>(p, sm, blockIdx.x, first_src, &bars[B_ROWS], &bars[B_GO], lane);
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                if (KIND == KASF_KIND_BONE) {
+                    mbar_wait_suspend(&bars[B_TAKEN], ph_taken);   // limb rows are in registers
+                    ph_taken ^= 1;
+                    gather_rows<MODE>(p, sm, tile, p.in, &bars[B_ROWS], nullptr, lane);
+                }
+#ifdef KASF_GATHER_SPIN
+                mbar_wait(&bars[B_OUT], ph_out);
+#else
+                mbar_wait_suspend(&bars[B_OUT], ph_out);
+#endif
+                ph_out ^= 1;
+                const int ntile = tile + (int)gridDim.x;
+                if (ntile < p.ntiles) gather_rows<MODE>(p, sm, ntile, first_src, &bars[B_ROWS], &bars[B_GO], lane);
+            }
+        } else if (warp == W_MMA && lane == 0) {
+            // ---- the only thread that issues tcgen05.mma
+            const uint32_t a_addr = smem_u32(sm + SM_ATILE), ring_addr = smem_u32(sm + SM_RING), hs_addr = smem_u32(sm + SM_AUX);
+            uint32_t cslot = 0, cph = 0, ph_a = 0, ph_hs0 = 0, ph_hs1 = 0;
+            auto chunk = [&](uint32_t tcol, uint32_t a_smem, bool acc) {
+                mbar_wait(&bars[B_FULL0 + cslot], cph);
+                tc_fence_after();
+                umma_tile_k128(tmem + tcol, a_smem, ring_addr + cslot * CHUNK_BYTES, 128, acc);
+                tc_commit(&bars[B_EMPTY0 + cslot]);
+                if (++cslot == RING) cslot = 0, cph ^= 1;
+            };
+            auto wait_a = [&]() {
+                mbar_wait(&bars[B_AREADY], ph_a);
+                ph_a ^= 1;
+                tc_fence_after();
+            };
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                if (KIND == KASF_KIND_ATTENTION) {
+                    wait_a();                                  // LN1(x)
+                    chunk(TM_MIX, a_addr, false);              // Q
+                    chunk(TM_K, a_addr, false);
+                    chunk(TM_V, a_addr, false);
+                    tc_commit(&bars[B_MMA]);
+                } else if (KIND == KASF_KIND_BONE) {
+                    wait_a();                                  // LN_limb(XL)
+                    chunk(TM_K, a_addr, false);
+                    chunk(TM_V, a_addr, false);
+                    tc_commit(&bars[B_MMA]);
+                    wait_a();                                  // LN1(x)
+                    chunk(TM_MIX, a_addr, false);              // Q
+                    tc_commit(&bars[B_MMA]);
+                } else {
+                    wait_a();                                  // z = LN1(x)
+                    chunk(TM_MIX, a_addr, false);              // U z
+                    tc_commit(&bars[B_MMA]);
+                }
+                wait_a();                                      // attention output | A_hat z
+                chunk(TM_MIX, a_addr, KIND == KASF_KIND_GRAPH);   // output projection | += (A_hat z) V^T
+                tc_commit(&bars[B_MMA]);
+                // ---- MLP: fc1 chunks run two ahead of the GELU epilogues, fc2 accumulates behind them
+                wait_a();                                      // LN2(x1)
+                chunk(TM_H0, a_addr, false);
+                tc_commit(&bars[B_HFULL0]);
+                chunk(TM_H1, a_addr, false);
+                tc_commit(&bars[B_HFULL1]);
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    const int buf = c & 1;
+                    if (buf) { mbar_wait(&bars[B_HSREADY1], ph_hs1); ph_hs1 ^= 1; }
+                    else { mbar_wait(&bars[B_HSREADY0], ph_hs0); ph_hs0 ^= 1; }
+                    tc_fence_after();
+                    if (c < 2) {                               // fc1 chunk c+2 first: the epilogue warps wait for it
+                        chunk(buf ? TM_H1 : TM_H0, a_addr, false);
+                        tc_commit(&bars[buf ? B_HFULL1 : B_HFULL0]);
+                    }
+                    chunk(TM_OUT, hs_addr + buf * TILE_BYTES, c > 0);
+                    if (c < 2) tc_commit(&bars[buf ? B_HSFREE1 : B_HSFREE0]);
+                    if (c == 3) tc_commit(&bars[B_OUT]);
                 }
             }
         }
@@ -515,21 +705,8 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
         e.half = warp >> 2;
         e.warp = warp;
         e.tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        uint32_t cslot = 0, cph = 0;   // ring read position (meaningful in thread 0)
         WaitBar mma{&bars[B_MMA], 0}, hfull0{&bars[B_HFULL0], 0}, hfull1{&bars[B_HFULL1], 0},
-            hsfree0{&bars[B_HSFREE0], 0}, hsfree1{&bars[B_HSFREE1], 0}, outb{&bars[B_OUT], 0};
-        const uint32_t a_addr = smem_u32(sm + SM_ATILE);
-        const uint32_t ring_addr = smem_u32(sm + SM_RING);
-        const uint32_t hs_addr = smem_u32(sm + SM_AUX);
-
-        // issue one weight chunk's MMA: D[tmem col] (+)= A(a_smem) * ring[slot]^T ; frees the slot when done
-        auto mma_chunk = [&](uint32_t tcol, uint32_t a_smem, bool acc) {
-            mbar_wait(&bars[B_FULL0 + cslot], cph);
-            tc_fence_after();
-            umma_tile_k128(tmem + tcol, a_smem, ring_addr + cslot * CHUNK_BYTES, 128, acc);
-            tc_commit(&bars[B_EMPTY0 + cslot]);
-            if (++cslot == RING) cslot = 0, cph ^= 1;
-        };
+            hsfree0{&bars[B_HSFREE0], 0}, hsfree1{&bars[B_HSFREE1], 0}, outb{&bars[B_OUT], 0}, rows{&bars[B_ROWS], 0};
 
         long long pt0 = p.prof ? clock64() : 0;
 #define PMARK(k)                                                      \
@@ -540,61 +717,30 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
             pt0 = pt1;                                                \
         }                                                             \
     } while (0)
-        // this thread's 64 columns of its row, straight from global memory: eight 256-bit loads = eight full
-        // sectors.  Issued one tile ahead (at the start of the previous tile's MLP).
-        auto fetch_row = [&](const float* src, long long tok, float(&dst)[64]) {
-            if (tok >= 0) {
-                const float* g = src + tok * D + e.half * 64;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) ldg256(g + c * 8, dst + c * 8);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 64; ++i) dst[i] = 0.f;
-            }
-        };
-        const float* first_src = KIND == KASF_KIND_BONE ? p.xl : p.in;
-        float xn[64];
-        long long tok_next = (int)blockIdx.x < p.ntiles ? row_token<MODE>(p, blockIdx.x, e.row) : -1;
-        fetch_row(first_src, tok_next, xn);
 
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-            // rows of this tile that carry tokens, and the group geometry
-            int gsize, nrows;
-            if (MODE == KASF_MODE_SPATIAL) {
-                gsize = J;
-                const long long left = (long long)p.B * p.T * J - (long long)tile * 119;
-                nrows = (int)(left < 119 ? left : 119);
-            } else {
-                gsize = p.T;
-                const long long left = (long long)p.B * J - (long long)tile * p.groups_per_tile;
-                nrows = (int)(left < p.groups_per_tile ? left : p.groups_per_tile) * p.T;
-            }
+            const int nrows = tile_rows<MODE>(p, tile);
+            const int gsize = MODE == KASF_MODE_SPATIAL ? J : p.T;
             const bool row_ok = e.row < nrows;
-            const long long tok = tok_next;     // token of this thread's row (-1: padding row)
+            const long long tok = row_ok ? row_token<MODE>(p, tile, e.row) : -1;
             float xv[64];
             float mean, rstd;
 
             if (KIND == KASF_KIND_BONE) {
-                // ---- K,V from the limb stream: LN_limb(XL) Wkv^T.  The residual rows of this tile are
-                //      requested first and land while LN_limb and the K,V MMAs run.
-                fetch_row(p.in, tok, xv);
-                ln_stats(sm, e, xn, mean, rstd);
-                ln_write<false>(sm, e, xn, mean, rstd, vec + V_NLW, vec + V_NLB, row_ok);
-                fence_proxy_async();
-                tc_fence_before();
-                csync();
-                if (tid == 0) {
-                    tc_fence_after();
-                    mma_chunk(TM_K, a_addr, false);
-                    mma_chunk(TM_V, a_addr, false);
-                    tc_commit(&bars[B_MMA]);
-                }
+                // ---- K,V from the limb stream: LN_limb(XL) Wkv^T
+                rows.wait();
+                read_staged(sm, e, xv, row_ok);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[B_TAKEN]);       // AUX may receive the residual rows now
+                ln_stats(sm, e, xv, mean, rstd);
+                ln_write<false>(sm, e, xv, mean, rstd, vec + V_NLW, vec + V_NLB, row_ok);
+                warp_arrive(&bars[B_AREADY], lane);
                 PMARK(0);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 64; ++i) xv[i] = xn[i];
             }
-            // ---- residual rows: registers -> tensor memory (resident); LN1 -> A operand
+            // ---- residual rows: staging -> registers -> tensor memory (resident); LN1 -> A operand
+            rows.wait();
+            PMARK(13);
+            read_staged(sm, e, xv, row_ok);
 #pragma unroll
             for (int b = 0; b < 2; ++b) {
                 uint32_t xr[32];
@@ -607,24 +753,14 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 mma.wait();                                // K,V complete: the A tile may be overwritten
                 tc_fence_after();
             }
+            if (KIND == KASF_KIND_GRAPH) csync();          // z (fp32) overwrites the staging rows of other threads
             ln_write<KIND == KASF_KIND_GRAPH>(sm, e, xv, mean, rstd, vec + V_N1W, vec + V_N1B, row_ok);
             tmem_st_wait();
-            fence_proxy_async();
-            tc_fence_before();
-            csync();
+            warp_arrive(&bars[B_AREADY], lane);
             PMARK(1);
 
             if (KIND != KASF_KIND_GRAPH) {
-                if (tid == 0) {
-                    tc_fence_after();
-                    mma_chunk(TM_MIX, a_addr, false);          // Q
-                    if (KIND == KASF_KIND_ATTENTION) {
-                        mma_chunk(TM_K, a_addr, false);
-                        mma_chunk(TM_V, a_addr, false);
-                    }
-                    tc_commit(&bars[B_MMA]);
-                }
-                mma.wait();
+                mma.wait();                                // Q (and K,V) in tensor memory
                 tc_fence_after();
                 PMARK(2);
                 // ---- Q,K,V: TMEM -> bf16 smem.  Q goes to the (now free) A tile in operand layout, where the
@@ -651,30 +787,19 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                             }
                         }
                     }
-                tc_fence_before();
-                csync();
+                csync();                                   // every warp reads the K|V rows of the others
                 PMARK(3);
-                attention_core<MODE>(sm, warp, lane, gsize, nrows);
-                fence_proxy_async();
-                csync();
+                attention_core<MODE, TC>(sm, warp, lane, gsize, nrows);
+                warp_arrive(&bars[B_AREADY], lane);
                 PMARK(4);
-                if (tid == 0) {
-                    tc_fence_after();
-                    mma_chunk(TM_MIX, a_addr, false);   // output projection (Q's columns are dead)
-                    tc_commit(&bars[B_MMA]);
-                }
-                mma.wait();
+                mma.wait();                                // output projection
                 tc_fence_after();
                 PMARK(5);
             } else {
                 // ================= GCN mixer =================
-                if (tid == 0) {
-                    tc_fence_after();
-                    mma_chunk(TM_MIX, a_addr, false);   // U z
-                    tc_commit(&bars[B_MMA]);
-                }
+                csync();                                   // z of the whole tile is in AUX
                 if (MODE == KASF_MODE_TEMPORAL) {
-                    similarity_topk(sm, warp, lane, p.T, nrows);
+                    similarity_topk<TC>(sm, warp, lane, p.T, nrows);
                     csync();
                     PMARK(6);
                 }
@@ -734,16 +859,10 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                     pk.z = pack_bf16(xv[c * 8 + 4], xv[c * 8 + 5]), pk.w = pack_bf16(xv[c * 8 + 6], xv[c * 8 + 7]);
                     *reinterpret_cast<uint4*>(sm + SM_ATILE + tile_off_bf16(e.row, e.half * 64 + c * 8)) = pk;
                 }
-                fence_proxy_async();
-                tc_fence_before();
-                csync();
+                pair_sync(e.warp);                         // the row sum written by the partner thread (half 0)
+                warp_arrive(&bars[B_AREADY], lane);
                 PMARK(7);
-                if (tid == 0) {
-                    tc_fence_after();
-                    mma_chunk(TM_MIX, a_addr, true);    // += (A_hat z) V^T
-                    tc_commit(&bars[B_MMA]);
-                }
-                mma.wait();
+                mma.wait();                                // += (A_hat z) V^T
                 tc_fence_after();
                 PMARK(8);
             }
@@ -793,61 +912,53 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
             ln_stats(sm, e, xv, mean, rstd);
             ln_write<false>(sm, e, xv, mean, rstd, vec + V_N2W, vec + V_N2B, row_ok);
             tmem_st_wait();
-            fence_proxy_async();
-            tc_fence_before();
-            csync();
+            warp_arrive(&bars[B_AREADY], lane);
             PMARK(10);
-            // ---- request the next tile's rows now: they arrive while the MLP runs
-            {
-                const int ntile = tile + (int)gridDim.x;
-                tok_next = ntile < p.ntiles ? row_token<MODE>(p, ntile, e.row) : -1;
-                fetch_row(first_src, tok_next, xn);
-            }
 
-            // ---- MLP: 4 hidden chunks of 128, software-pipelined over two TMEM / smem buffers
-            if (tid == 0) {
-                tc_fence_after();
-                mma_chunk(TM_H0, a_addr, false);
-                tc_commit(&bars[B_HFULL0]);
-            }
+            // ---- MLP epilogues: hidden chunk c (fc1 accumulator in TMEM) -> 2*GELU -> bf16 A operand tile AUX[c & 1]
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 const int buf = c & 1;
-                if (tid == 0 && c + 1 < 4) {
-                    mma_chunk(buf ? TM_H0 : TM_H1, a_addr, false);
-                    tc_commit(&bars[buf ? B_HFULL0 : B_HFULL1]);
-                }
                 if (buf) hfull1.wait(); else hfull0.wait();
                 tc_fence_after();
                 if (c >= 2) { if (buf) hsfree1.wait(); else hsfree0.wait(); }
-                // GELU epilogue: TMEM hidden chunk -> bf16 A operand tile in AUX[buf]
+                uint32_t acc[2][32];
+                tmem_ld32(e.tbase + (buf ? TM_H1 : TM_H0) + e.half * 64, acc[0]);
+                tmem_ld32(e.tbase + (buf ? TM_H1 : TM_H0) + e.half * 64 + 32, acc[1]);
+                tmem_ld_wait();
+                // two-stage software pipeline over groups of 8 columns: the tanh arguments of group g+1 are computed
+                // while the MUFU results of group g are in flight (the compiler's own schedule consumed each result
+                // a few instructions after issuing it: 1960 vs 1440 cycles per chunk, scripts/micro/gelu_epi.cu)
+                const float* b1 = vec + V_B1 + c * 128 + e.half * 64;
+                uint8_t* hs = sm + SM_AUX + buf * TILE_BYTES;
+                float v[2][8], w[2][8];
+                auto stage1 = [&](int g, int s2) {
+                    const float4 ba = *reinterpret_cast<const float4*>(b1 + g * 8);
+                    const float4 bb = *reinterpret_cast<const float4*>(b1 + g * 8 + 4);
+                    const uint32_t* a8 = &acc[g >> 2][(g & 3) * 8];
+                    v[s2][0] = __uint_as_float(a8[0]) + ba.x, v[s2][1] = __uint_as_float(a8[1]) + ba.y;
+                    v[s2][2] = __uint_as_float(a8[2]) + ba.z, v[s2][3] = __uint_as_float(a8[3]) + ba.w;
+                    v[s2][4] = __uint_as_float(a8[4]) + bb.x, v[s2][5] = __uint_as_float(a8[5]) + bb.y;
+                    v[s2][6] = __uint_as_float(a8[6]) + bb.z, v[s2][7] = __uint_as_float(a8[7]) + bb.w;
 #pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    uint32_t acc[32];
-                    tmem_ld32(e.tbase + (buf ? TM_H1 : TM_H0) + e.half * 64 + b * 32, acc);
-                    tmem_ld_wait();
-                    const float* b1 = vec + V_B1 + c * 128 + e.half * 64 + b * 32;
+                    for (int i = 0; i < 8; ++i) w[s2][i] = gelu2_arg(v[s2][i]);
+                };
+                stage1(0, 0);
 #pragma unroll
-                    for (int c8 = 0; c8 < 4; ++c8) {
-                        const float4 ba = *reinterpret_cast<const float4*>(b1 + c8 * 8);
-                        const float4 bb = *reinterpret_cast<const float4*>(b1 + c8 * 8 + 4);
-                        uint4 pk;
-                        pk.x = pack_bf16(gelu2_erf(__uint_as_float(acc[c8 * 8 + 0]) + ba.x), gelu2_erf(__uint_as_float(acc[c8 * 8 + 1]) + ba.y));
-                        pk.y = pack_bf16(gelu2_erf(__uint_as_float(acc[c8 * 8 + 2]) + ba.z), gelu2_erf(__uint_as_float(acc[c8 * 8 + 3]) + ba.w));
-                        pk.z = pack_bf16(gelu2_erf(__uint_as_float(acc[c8 * 8 + 4]) + bb.x), gelu2_erf(__uint_as_float(acc[c8 * 8 + 5]) + bb.y));
-                        pk.w = pack_bf16(gelu2_erf(__uint_as_float(acc[c8 * 8 + 6]) + bb.z), gelu2_erf(__uint_as_float(acc[c8 * 8 + 7]) + bb.w));
-                        *reinterpret_cast<uint4*>(sm + SM_AUX + buf * TILE_BYTES + tile_off_bf16(e.row, e.half * 64 + b * 32 + c8 * 8)) = pk;
-                    }
+                for (int g = 0; g < 8; ++g) {
+                    const int s2 = g & 1;
+                    float t[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) t[i] = gelu2_tanh(w[s2][i]);
+                    if (g + 1 < 8) stage1(g + 1, s2 ^ 1);
+                    uint4 pk;
+                    pk.x = pack_bf16(fmaf(v[s2][0], t[0], v[s2][0]), fmaf(v[s2][1], t[1], v[s2][1]));
+                    pk.y = pack_bf16(fmaf(v[s2][2], t[2], v[s2][2]), fmaf(v[s2][3], t[3], v[s2][3]));
+                    pk.z = pack_bf16(fmaf(v[s2][4], t[4], v[s2][4]), fmaf(v[s2][5], t[5], v[s2][5]));
+                    pk.w = pack_bf16(fmaf(v[s2][6], t[6], v[s2][6]), fmaf(v[s2][7], t[7], v[s2][7]));
+                    *reinterpret_cast<uint4*>(hs + tile_off_bf16(e.row, e.half * 64 + g * 8)) = pk;
                 }
-                fence_proxy_async();
-                tc_fence_before();
-                csync();
-                if (tid == 0) {
-                    tc_fence_after();
-                    mma_chunk(TM_OUT, hs_addr + buf * TILE_BYTES, c > 0);
-                    if (c < 2) tc_commit(&bars[buf ? B_HSFREE1 : B_HSFREE0]);
-                    if (c == 3) tc_commit(&bars[B_OUT]);
-                }
+                warp_arrive(&bars[buf ? B_HSREADY1 : B_HSREADY0], lane);
             }
             outb.wait();
             tc_fence_after();
@@ -880,7 +991,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 }
             }
             // (no CTA barrier here: the next tile's first shared-memory writes touch buffers whose last readers
-            //  were MMAs already observed complete by every thread, and its first MMA follows a csync)
+            //  were MMAs already observed complete by every thread, and its MMAs wait for AREADY)
             PMARK(12);
         }
     }
@@ -889,11 +1000,11 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-template <int KIND, int MODE>
+template <int KIND, int MODE, int TC>
 static int launch_one(const ModParams& p, cudaStream_t st) {
-    cudaFuncSetAttribute(former_module_kernel<KIND, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+    cudaFuncSetAttribute(former_module_kernel<KIND, MODE, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
     const int grid = p.ntiles < 148 ? p.ntiles : 148;
-    former_module_kernel<KIND, MODE><<<grid, MOD_THREADS, SM_TOTAL, st>>>(p);
+    former_module_kernel<KIND, MODE, TC><<<grid, MOD_THREADS, SM_TOTAL, st>>>(p);
     return cuda_status();
 }
 
@@ -913,16 +1024,21 @@ int launch_former_module(const uint8_t* blob, int layer, int kind, int mode, con
     p.B = B;
     p.T = T;
     p.prof = prof;
+    int tc = 0;
     if (mode == KASF_MODE_SPATIAL) {
         p.groups_per_tile = 7;
         p.ntiles = (int)(((long long)B * T + 6) / 7);
     } else {
         p.groups_per_tile = 128 / T;
         p.ntiles = (int)(((long long)B * J + p.groups_per_tile - 1) / p.groups_per_tile);
+        tc = T <= 32 ? 0 : (T <= 64 ? 1 : 2);
     }
-#define KASF_CASE(K, M) \
-    if (kind == K && mode == M) return launch_one<K, M>(p, st);
-    KASF_CASE(0, 0) KASF_CASE(0, 1) KASF_CASE(1, 0) KASF_CASE(1, 1) KASF_CASE(2, 0) KASF_CASE(2, 1)
+#define KASF_CASE(K, M, C) \
+    if (kind == K && mode == M && tc == C) return launch_one<K, M, C>(p, st);
+    KASF_CASE(0, 0, 0) KASF_CASE(1, 0, 0) KASF_CASE(2, 0, 0)
+    KASF_CASE(0, 1, 0) KASF_CASE(0, 1, 1) KASF_CASE(0, 1, 2)
+    KASF_CASE(1, 1, 0) KASF_CASE(1, 1, 1) KASF_CASE(1, 1, 2)
+    KASF_CASE(2, 1, 0) KASF_CASE(2, 1, 1) KASF_CASE(2, 1, 2)
 #undef KASF_CASE
     return KASF_EINVAL;
 }

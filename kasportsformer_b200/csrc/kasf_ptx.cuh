@@ -165,6 +165,10 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src,
                  "r"(src_bytes)
                  : "memory");
 }
+// the mbarrier receives one arrival (counted in its init count) once all prior cp.async of this thread landed
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -207,12 +211,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ void umma_tile_k128(uint32_t tmem_d, uint32_t a_smem, uint32_t b_smem, uint32_t N,
                                                bool accumulate_first) {
     const uint32_t idesc = umma_idesc_bf16(128, N);
+    // the start-address field (16-byte units) is the only part of the descriptor that moves with the K-step
+    const uint64_t da = umma_desc_sw128(a_smem), db = umma_desc_sw128(b_smem);
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
         // sub-tile (ks / 4), 32 bytes (16 bf16) per K-step inside the 128-byte swizzled row
-        const uint32_t koff = (ks >> 2) * 16384u + (ks & 3) * 32u;
-        umma_bf16(tmem_d, umma_desc_sw128(a_smem + koff), umma_desc_sw128(b_smem + koff), idesc,
-                  (accumulate_first || ks > 0) ? 1u : 0u);
+        const uint64_t koff = (uint64_t)(((ks >> 2) * 16384u + (ks & 3) * 32u) >> 4);
+        umma_bf16(tmem_d, da + koff, db + koff, idesc, (accumulate_first || ks > 0) ? 1u : 0u);
     }
 }
 
