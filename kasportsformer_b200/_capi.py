@@ -265,7 +265,8 @@ def former_module(cfg, blob, layer, kind, mode, v, XL=None, out=None):
 
 
 PHASES = ["limb_kv", "load_ln1", "qkv_mma_wait", "qkv_drain", "attention", "proj_mma_wait", "similarity",
-          "aggregation", "v_mma_wait", "mixer_epilogue", "ln2", "mlp", "out_epilogue", "rows_wait"]
+          "aggregation", "v_mma_wait", "mixer_epilogue", "ln2", "mlp", "out_epilogue", "rows_wait",
+          "gather_issue", "gather_landed"]
 
 
 def former_module_phases(cfg, blob, layer, kind, mode, v, XL=None):

@@ -41,14 +41,22 @@ __constant__ int c_deg[17] = KASF_DEG;
 __constant__ float c_rsd[5] = {0.f, 1.0f, 0.70710678118654752440f, 0.57735026918962576451f, 0.5f};
 
 constexpr int CW = 8;                         // compute warps (TMEM epilogues, LayerNorm, mixer cores)
-constexpr int MOD_THREADS = (CW + 4) * 32;    // + service warpgroup: weight producer, MMA issuer, row gatherer
-constexpr int W_PRODUCER = CW, W_MMA = CW + 1, W_GATHER = CW + 2;
+constexpr int MOD_THREADS = (CW + 4) * 32;    // + service warpgroup: weight producer, MMA issuer (+ 2 register donors)
+constexpr int W_PRODUCER = CW, W_MMA = CW + 1;
 constexpr int RING = 3;
-constexpr uint32_t ROW_PITCH = 528;                   // staged fp32 row: 512 B + 16 B pad (conflict-free thread-per-row reads)
-constexpr uint32_t SM_AUX = 0;
-constexpr uint32_t AUX_BYTES = 128 * ROW_PITCH;       // 67584 (a multiple of 1024)
-constexpr uint32_t SM_ATILE = SM_AUX + AUX_BYTES;
-constexpr uint32_t SM_RING = SM_ATILE + 32768;
+// Three 32 KB buffers:
+//   B0 ....... A operand tile: LN1 / LN_limb / A_hat z, then Q -> attention output, then LN2 (fc1)
+//   B1|B2 .... staged fp32 rows (gather), then bf16 K|V or fp32 z (GCN), then the two hidden tiles of the MLP
+constexpr uint32_t SM_B0 = 0, SM_B1 = 32768, SM_B2 = 65536;
+constexpr uint32_t SM_STAGE = SM_B1;                  // fp32 [128][128], XOR-swizzled 16-byte chunks (f32_off)
+constexpr uint32_t SM_Z = SM_B1;                      // same layout (GCN: z = LN1(x) in fp32)
+constexpr uint32_t SM_KV = SM_B1;                     // bf16 K|V, row pitch 512 B (f32_off)
+constexpr uint32_t SM_HS = SM_B1;                     // hidden tiles 0, 1 (operand layout)
+constexpr uint32_t SM_A0 = SM_B0, SM_A1 = SM_B0;      // A operand tile (one buffer; the two names mark the two uses)
+#ifndef KASF_RING_SHIFT
+#define KASF_RING_SHIFT 0
+#endif
+constexpr uint32_t SM_RING = 98304 + KASF_RING_SHIFT;
 constexpr uint32_t SM_VEC = SM_RING + RING * 32768;
 constexpr uint32_t SM_PART = SM_VEC + 10240;          // float2 [128][2]
 constexpr uint32_t SM_ADJ = SM_PART + 2048;           // u32 [128][4]
@@ -58,7 +66,6 @@ constexpr uint32_t SM_BARS = SM_RSD + 512;
 constexpr uint32_t SM_TOTAL = SM_BARS + 256;
 static_assert(SM_TOTAL <= 232448, "shared memory budget");
 static_assert(MOD_VEC_BYTES == 10240, "vector block size");
-static_assert(AUX_BYTES % 1024 == 0 && AUX_BYTES >= 65536, "operand tiles behind AUX must stay 1024-byte aligned");
 
 constexpr uint32_t TM_MIX = 0, TM_K = 128, TM_V = 256, TM_X = 384;   // mixer phase (Q lives at TM_MIX)
 constexpr uint32_t TM_H0 = 0, TM_H1 = 128, TM_OUT = 256;            // MLP phase
@@ -66,10 +73,9 @@ constexpr uint32_t TM_H0 = 0, TM_H1 = 128, TM_OUT = 256;            // MLP phase
 // mbarriers.  Ring: FULL (bulk-copy bytes) / EMPTY (tcgen05.commit).  Compute warps -> MMA warp: AREADY (the A
 // operand tile is written), HSREADY (hidden tile c written, hidden accumulator drained).  MMA warp -> compute
 // warps: MMA (mixer projections done), HFULL (fc1 chunk in TMEM), HSFREE (fc2 has read the hidden tile),
-// OUT (fc2 complete).  Gather warp <-> compute warps: ROWS (staged rows landed), TAKEN (staged rows consumed).
-// Gather warp -> weight producer: GO (the first rows of the tile have landed: weights may use the L2 port now).
+// OUT (fc2 complete).  ROWS: the cp.async row gather of a tile has landed (one arrival per compute thread).
 enum { B_FULL0 = 0, B_EMPTY0 = RING, B_AREADY = 2 * RING, B_MMA, B_HFULL0, B_HFULL1, B_HSREADY0, B_HSREADY1,
-       B_HSFREE0, B_HSFREE1, B_OUT, B_ROWS, B_TAKEN, B_GO, B_COUNT };
+       B_HSFREE0, B_HSFREE1, B_OUT, B_ROWS, B_COUNT };
 static_assert(B_COUNT * 8 + 8 <= 256, "barrier block");
 
 struct ModParams {
@@ -174,8 +180,8 @@ __device__ __forceinline__ void ln_stats(uint8_t* sm, const EpiMap& e, const flo
 
 // z = (x - mean) * rstd * gamma + beta for this thread's 64 columns -> bf16 A operand tile (+ fp32 copy in AUX)
 template <bool Z_TO_AUX>
-__device__ __forceinline__ void ln_write(uint8_t* sm, const EpiMap& e, const float (&xv)[64], float mean, float rstd,
-                                         const float* gamma, const float* beta, bool ok) {
+__device__ __forceinline__ void ln_write(uint8_t* sm, uint32_t a_tile, const EpiMap& e, const float (&xv)[64], float mean,
+                                         float rstd, const float* gamma, const float* beta, bool ok) {
     const float nm = -mean * rstd;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -197,10 +203,10 @@ __device__ __forceinline__ void ln_write(uint8_t* sm, const EpiMap& e, const flo
         }
         uint4 pk;
         pk.x = pack_bf16(z[0], z[1]), pk.y = pack_bf16(z[2], z[3]), pk.z = pack_bf16(z[4], z[5]), pk.w = pack_bf16(z[6], z[7]);
-        *reinterpret_cast<uint4*>(sm + SM_ATILE + tile_off_bf16(e.row, col)) = pk;
+        *reinterpret_cast<uint4*>(sm + a_tile + tile_off_bf16(e.row, col)) = pk;
         if (Z_TO_AUX) {
-            *reinterpret_cast<float4*>(sm + SM_AUX + f32_off(e.row, col >> 2)) = make_float4(z[0], z[1], z[2], z[3]);
-            *reinterpret_cast<float4*>(sm + SM_AUX + f32_off(e.row, (col >> 2) + 1)) = make_float4(z[4], z[5], z[6], z[7]);
+            *reinterpret_cast<float4*>(sm + SM_Z + f32_off(e.row, col >> 2)) = make_float4(z[0], z[1], z[2], z[3]);
+            *reinterpret_cast<float4*>(sm + SM_Z + f32_off(e.row, (col >> 2) + 1)) = make_float4(z[4], z[5], z[6], z[7]);
         }
     }
 }
@@ -239,7 +245,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // constant (17 joints), so key tiles past the group and the key masks fold away.
 template <int MAXNT, int U, int GS>   // MAXNT: key tiles of 8 held in registers (gsize <= 8 * MAXNT)
 __device__ __forceinline__ void attention_core_impl(uint8_t* sm, int warp, int lane, int gsize_rt, int nrows) {
-    const uint32_t q_base = smem_u32(sm + SM_ATILE), kv_base = smem_u32(sm + SM_AUX);
+    const uint32_t q_base = smem_u32(sm + SM_A0), kv_base = smem_u32(sm + SM_KV);
     const int gsize = GS ? GS : gsize_rt;
     const int ngroups = nrows / gsize;
     const int mtiles = (gsize + 15) >> 4;
@@ -358,9 +364,9 @@ __device__ __forceinline__ void attention_core_impl(uint8_t* sm, int warp, int l
                 // columns h*16 + dn*8 + ..: the next 16-byte chunk of the row, i.e. chunk index ^ 1 after swizzling
                 const uint32_t x0 = dn ? (o0 ^ 16u) : o0, x1 = dn ? (o1 ^ 16u) : o1;
                 if (live[u] && qr0 < gsize)
-                    *reinterpret_cast<uint32_t*>(sm + SM_ATILE + x0) = pack_bf16(o[u][dn][0] * i0, o[u][dn][1] * i0);
+                    *reinterpret_cast<uint32_t*>(sm + SM_A0 + x0) = pack_bf16(o[u][dn][0] * i0, o[u][dn][1] * i0);
                 if (live[u] && qr1 < gsize)
-                    *reinterpret_cast<uint32_t*>(sm + SM_ATILE + x1) = pack_bf16(o[u][dn][2] * i1, o[u][dn][3] * i1);
+                    *reinterpret_cast<uint32_t*>(sm + SM_A0 + x1) = pack_bf16(o[u][dn][2] * i1, o[u][dn][3] * i1);
             }
         }
     }
@@ -401,10 +407,10 @@ __device__ __forceinline__ void similarity_topk_impl(uint8_t* sm, int warp, int 
         for (int ks = 0; ks < 16; ++ks) {           // K = 128 in steps of 8
             // A fragment: (row g8 | g8+8, k = 8 ks + t4 | + 4)
             float av[4];
-            av[0] = *reinterpret_cast<const float*>(sm + SM_AUX + f32_off(ra, 2 * ks) + t4 * 4);
-            av[1] = *reinterpret_cast<const float*>(sm + SM_AUX + f32_off(rb, 2 * ks) + t4 * 4);
-            av[2] = *reinterpret_cast<const float*>(sm + SM_AUX + f32_off(ra, 2 * ks + 1) + t4 * 4);
-            av[3] = *reinterpret_cast<const float*>(sm + SM_AUX + f32_off(rb, 2 * ks + 1) + t4 * 4);
+            av[0] = *reinterpret_cast<const float*>(sm + SM_Z + f32_off(ra, 2 * ks) + t4 * 4);
+            av[1] = *reinterpret_cast<const float*>(sm + SM_Z + f32_off(rb, 2 * ks) + t4 * 4);
+            av[2] = *reinterpret_cast<const float*>(sm + SM_Z + f32_off(ra, 2 * ks + 1) + t4 * 4);
+            av[3] = *reinterpret_cast<const float*>(sm + SM_Z + f32_off(rb, 2 * ks + 1) + t4 * 4);
             uint32_t ah[4], al[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -416,8 +422,8 @@ __device__ __forceinline__ void similarity_topk_impl(uint8_t* sm, int warp, int 
                 if (nt < nkt) {
                     // B fragment: (k = 8 ks + t4 | + 4, n = key 8 nt + g8)
                     const int rj = min(gr0 + 8 * nt + g8, 127);
-                    const float b0 = *reinterpret_cast<const float*>(sm + SM_AUX + f32_off(rj, 2 * ks) + t4 * 4);
-                    const float b1 = *reinterpret_cast<const float*>(sm + SM_AUX + f32_off(rj, 2 * ks + 1) + t4 * 4);
+                    const float b0 = *reinterpret_cast<const float*>(sm + SM_Z + f32_off(rj, 2 * ks) + t4 * 4);
+                    const float b1 = *reinterpret_cast<const float*>(sm + SM_Z + f32_off(rj, 2 * ks + 1) + t4 * 4);
                     const uint32_t bh0 = __float_as_uint(b0) & 0xffffe000u, bh1 = __float_as_uint(b1) & 0xffffe000u;
                     const uint32_t bl0 = __float_as_uint(b0 - __uint_as_float(bh0));
                     const uint32_t bl1 = __float_as_uint(b1 - __uint_as_float(bh1));
@@ -497,35 +503,31 @@ __device__ __forceinline__ int tile_rows(const ModParams& p, int tile) {
     }
 }
 
-// Row gather of one tile by the gather warp: one coalesced 512-byte cp.async (LDGSTS, 16 B per lane) per row into
-// the padded staging rows of AUX; every lane then attaches the completion of its copies to `bar` (32 arrivals).
-// No registers hold data and the latency is off the compute warps' critical path.
+// Row gather of a tile, issued by the compute warps themselves (a service warp gets an LDGSTS through every ~75
+// cycles next to busy compute warps -- measured -- while 8 warps x 16 instructions are gone in a few hundred):
+// warp w copies rows w, w+8, ..., one coalesced 512-byte cp.async (16 B per lane) per row into the staging buffer
+// (swizzled like every fp32 tile, so the thread-per-row reads are conflict-free); every lane then attaches the
+// completion of its copies to `bar`.  Issued right after fc2 completes: the rows land behind the output epilogue.
 template <int MODE>
 __device__ __forceinline__ void gather_rows(const ModParams& p, uint8_t* sm, int tile, const float* src, uint64_t* bar,
-                                            uint64_t* bar2, int lane) {
+                                            int warp, int lane) {
     const int n = tile_rows<MODE>(p, tile);
-    uint8_t* dst = sm + SM_AUX + lane * 16;
     if (MODE == KASF_MODE_SPATIAL) {
         const float* g = src + (long long)tile * 119 * D + lane * 4;
 #pragma unroll 4
-        for (int r = 0; r < n; ++r) cp_async16(dst + r * ROW_PITCH, g + (size_t)r * D, 16u);
+        for (int r = warp; r < n; r += CW) cp_async16(sm + SM_STAGE + f32_off(r, lane), g + (size_t)r * D, 16u);
     } else {
-        // lane l knows the tokens of rows l, l+32, l+64, l+96; they are broadcast row by row
-        int mytok[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) mytok[k] = lane + 32 * k < n ? (int)row_token<MODE>(p, tile, lane + 32 * k) : 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int cnt = min(32, n - 32 * k);
+        // lane l (< 16) knows the token of row warp + 8 l; broadcast row by row
+        const int myrow = warp + CW * (lane & 15);
+        const int mytok = myrow < n ? (int)row_token<MODE>(p, tile, myrow) : 0;
 #pragma unroll 4
-            for (int l = 0; l < cnt; ++l) {
-                const int tok = __shfl_sync(0xffffffffu, mytok[k], l);
-                cp_async16(dst + (32 * k + l) * ROW_PITCH, src + (size_t)tok * D + lane * 4, 16u);
-            }
+        for (int k = 0; k < 16; ++k) {
+            const int tok = __shfl_sync(0xffffffffu, mytok, k);
+            const int r = warp + CW * k;
+            if (r < n) cp_async16(sm + SM_STAGE + f32_off(r, lane), src + (size_t)tok * D + lane * 4, 16u);
         }
     }
     cp_async_mbar_arrive(bar);
-    if (bar2) cp_async_mbar_arrive(bar2);
 }
 
 // this thread's 64 staged values of its row (zeros for padding rows)
@@ -533,7 +535,7 @@ __device__ __forceinline__ void read_staged(const uint8_t* sm, const EpiMap& e, 
     if (ok) {
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
-            const float4 v = *reinterpret_cast<const float4*>(sm + SM_AUX + e.row * ROW_PITCH + (e.half * 16 + c) * 16);
+            const float4 v = *reinterpret_cast<const float4*>(sm + SM_STAGE + f32_off(e.row, e.half * 16 + c));
             xv[c * 4] = v.x, xv[c * 4 + 1] = v.y, xv[c * 4 + 2] = v.z, xv[c * 4 + 3] = v.w;
         }
     } else {
@@ -568,8 +570,8 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
     if (tid == 0) {
         if ((smem_u32(sm) & 1023u) != 0) __trap();
         for (int i = 0; i < B_COUNT; ++i) {
-            const bool by_warps = i == B_AREADY || i == B_HSREADY0 || i == B_HSREADY1 || i == B_TAKEN;
-            mbar_init(&bars[i], by_warps ? CW : (i == B_ROWS || i == B_GO ? 32 : 1));
+            const bool by_warps = i == B_AREADY || i == B_HSREADY0 || i == B_HSREADY1;
+            mbar_init(&bars[i], by_warps ? CW : (i == B_ROWS ? CW * 32 : 1));
         }
         fence_mbar_init();
     }
@@ -598,12 +600,8 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
         if (warp == W_PRODUCER) {
             // ---- weight chunks: L2 -> ring slots (bulk copies, MMA-ready swizzled images)
             if (lane == 0) {
-                // The SM's L2 port (~40 B/clk when every SM streams) is the scarce resource at a tile boundary: the
-                // 60 KB of rows the next LayerNorm waits for go first, the 96 KB of ring refills after them.
-                uint32_t slot = 0, ph = 0, ph_go = 0;
+                uint32_t slot = 0, ph = 0;
                 for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                    mbar_wait_suspend(&bars[B_GO], ph_go);
-                    ph_go ^= 1;
 #pragma unroll 1
                     for (int i = 0; i < NCH; ++i) {
                         const int ci = KIND == KASF_KIND_ATTENTION ? ORD_ATT[i] : (KIND == KASF_KIND_BONE ? ORD_BONE[i] : ORD_GCN[i]);
@@ -615,29 +613,10 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                     }
                 }
             }
-        } else if (warp == W_GATHER) {
-            // ---- residual (and limb) rows of the NEXT tile -> AUX as soon as fc2 of the current tile has
-            //      finished reading its hidden tiles: the gather overlaps the output epilogue
-            uint32_t ph_out = 0, ph_taken = 0;
-            if ((int)blockIdx.x < p.ntiles) gather_rows<MODE>(p, sm, blockIdx.x, first_src, &bars[B_ROWS], &bars[B_GO], lane);
-            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                if (KIND == KASF_KIND_BONE) {
-                    mbar_wait_suspend(&bars[B_TAKEN], ph_taken);   // limb rows are in registers
-                    ph_taken ^= 1;
-                    gather_rows<MODE>(p, sm, tile, p.in, &bars[B_ROWS], nullptr, lane);
-                }
-#ifdef KASF_GATHER_SPIN
-                mbar_wait(&bars[B_OUT], ph_out);
-#else
-                mbar_wait_suspend(&bars[B_OUT], ph_out);
-#endif
-                ph_out ^= 1;
-                const int ntile = tile + (int)gridDim.x;
-                if (ntile < p.ntiles) gather_rows<MODE>(p, sm, ntile, first_src, &bars[B_ROWS], &bars[B_GO], lane);
-            }
         } else if (warp == W_MMA && lane == 0) {
             // ---- the only thread that issues tcgen05.mma
-            const uint32_t a_addr = smem_u32(sm + SM_ATILE), ring_addr = smem_u32(sm + SM_RING), hs_addr = smem_u32(sm + SM_AUX);
+            const uint32_t a0_addr = smem_u32(sm + SM_A0), a1_addr = smem_u32(sm + SM_A1), ring_addr = smem_u32(sm + SM_RING),
+                           hs_addr = smem_u32(sm + SM_HS);
             uint32_t cslot = 0, cph = 0, ph_a = 0, ph_hs0 = 0, ph_hs1 = 0;
             auto chunk = [&](uint32_t tcol, uint32_t a_smem, bool acc) {
                 mbar_wait(&bars[B_FULL0 + cslot], cph);
@@ -654,31 +633,31 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
                 if (KIND == KASF_KIND_ATTENTION) {
                     wait_a();                                  // LN1(x)
-                    chunk(TM_MIX, a_addr, false);              // Q
-                    chunk(TM_K, a_addr, false);
-                    chunk(TM_V, a_addr, false);
+                    chunk(TM_MIX, a1_addr, false);             // Q
+                    chunk(TM_K, a1_addr, false);
+                    chunk(TM_V, a1_addr, false);
                     tc_commit(&bars[B_MMA]);
                 } else if (KIND == KASF_KIND_BONE) {
                     wait_a();                                  // LN_limb(XL)
-                    chunk(TM_K, a_addr, false);
-                    chunk(TM_V, a_addr, false);
+                    chunk(TM_K, a1_addr, false);
+                    chunk(TM_V, a1_addr, false);
                     tc_commit(&bars[B_MMA]);
                     wait_a();                                  // LN1(x)
-                    chunk(TM_MIX, a_addr, false);              // Q
+                    chunk(TM_MIX, a1_addr, false);             // Q
                     tc_commit(&bars[B_MMA]);
                 } else {
                     wait_a();                                  // z = LN1(x)
-                    chunk(TM_MIX, a_addr, false);              // U z
+                    chunk(TM_MIX, a1_addr, false);             // U z
                     tc_commit(&bars[B_MMA]);
                 }
-                wait_a();                                      // attention output | A_hat z
-                chunk(TM_MIX, a_addr, KIND == KASF_KIND_GRAPH);   // output projection | += (A_hat z) V^T
+                wait_a();                                      // attention output (B0) | A_hat z (B2)
+                chunk(TM_MIX, KIND == KASF_KIND_GRAPH ? a1_addr : a0_addr, KIND == KASF_KIND_GRAPH);   // proj | += (A_hat z) V^T
                 tc_commit(&bars[B_MMA]);
                 // ---- MLP: fc1 chunks run two ahead of the GELU epilogues, fc2 accumulates behind them
                 wait_a();                                      // LN2(x1)
-                chunk(TM_H0, a_addr, false);
+                chunk(TM_H0, a0_addr, false);
                 tc_commit(&bars[B_HFULL0]);
-                chunk(TM_H1, a_addr, false);
+                chunk(TM_H1, a0_addr, false);
                 tc_commit(&bars[B_HFULL1]);
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
@@ -687,7 +666,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                     else { mbar_wait(&bars[B_HSREADY0], ph_hs0); ph_hs0 ^= 1; }
                     tc_fence_after();
                     if (c < 2) {                               // fc1 chunk c+2 first: the epilogue warps wait for it
-                        chunk(buf ? TM_H1 : TM_H0, a_addr, false);
+                        chunk(buf ? TM_H1 : TM_H0, a0_addr, false);
                         tc_commit(&bars[buf ? B_HFULL1 : B_HFULL0]);
                     }
                     chunk(TM_OUT, hs_addr + buf * TILE_BYTES, c > 0);
@@ -718,6 +697,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
         }                                                             \
     } while (0)
 
+        gather_rows<MODE>(p, sm, blockIdx.x, first_src, &bars[B_ROWS], warp, lane);
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
             const int nrows = tile_rows<MODE>(p, tile);
             const int gsize = MODE == KASF_MODE_SPATIAL ? J : p.T;
@@ -730,10 +710,10 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 // ---- K,V from the limb stream: LN_limb(XL) Wkv^T
                 rows.wait();
                 read_staged(sm, e, xv, row_ok);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars[B_TAKEN]);       // AUX may receive the residual rows now
+                csync();                                   // every limb row is in registers: the staging buffer
+                gather_rows<MODE>(p, sm, tile, p.in, &bars[B_ROWS], warp, lane);   // receives the residual rows
                 ln_stats(sm, e, xv, mean, rstd);
-                ln_write<false>(sm, e, xv, mean, rstd, vec + V_NLW, vec + V_NLB, row_ok);
+                ln_write<false>(sm, SM_A1, e, xv, mean, rstd, vec + V_NLW, vec + V_NLB, row_ok);
                 warp_arrive(&bars[B_AREADY], lane);
                 PMARK(0);
             }
@@ -754,7 +734,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 tc_fence_after();
             }
             if (KIND == KASF_KIND_GRAPH) csync();          // z (fp32) overwrites the staging rows of other threads
-            ln_write<KIND == KASF_KIND_GRAPH>(sm, e, xv, mean, rstd, vec + V_N1W, vec + V_N1B, row_ok);
+            ln_write<KIND == KASF_KIND_GRAPH>(sm, SM_A1, e, xv, mean, rstd, vec + V_N1W, vec + V_N1B, row_ok);
             tmem_st_wait();
             warp_arrive(&bars[B_AREADY], lane);
             PMARK(1);
@@ -780,10 +760,10 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                             pk.z = pack_bf16(__uint_as_float(acc[c * 8 + 4]), __uint_as_float(acc[c * 8 + 5]));
                             pk.w = pack_bf16(__uint_as_float(acc[c * 8 + 6]), __uint_as_float(acc[c * 8 + 7]));
                             if (qkv == 0) {
-                                *reinterpret_cast<uint4*>(sm + SM_ATILE + tile_off_bf16(e.row, e.half * 64 + b * 32 + c * 8)) = pk;
+                                *reinterpret_cast<uint4*>(sm + SM_A0 + tile_off_bf16(e.row, e.half * 64 + b * 32 + c * 8)) = pk;
                             } else {
                                 const uint32_t chunk = (qkv - 1) * 16 + e.half * 8 + b * 4 + c;
-                                *reinterpret_cast<uint4*>(sm + SM_AUX + f32_off(e.row, chunk)) = pk;
+                                *reinterpret_cast<uint4*>(sm + SM_KV + f32_off(e.row, chunk)) = pk;
                             }
                         }
                     }
@@ -819,7 +799,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                             rs += cf;
 #pragma unroll
                             for (int c = 0; c < 16; ++c) {
-                                const float4 z = *reinterpret_cast<const float4*>(sm + SM_AUX + f32_off(base + nb, e.half * 16 + c));
+                                const float4 z = *reinterpret_cast<const float4*>(sm + SM_Z + f32_off(base + nb, e.half * 16 + c));
                                 xv[c * 4] = fmaf(cf, z.x, xv[c * 4]), xv[c * 4 + 1] = fmaf(cf, z.y, xv[c * 4 + 1]);
                                 xv[c * 4 + 2] = fmaf(cf, z.z, xv[c * 4 + 2]), xv[c * 4 + 3] = fmaf(cf, z.w, xv[c * 4 + 3]);
                             }
@@ -841,7 +821,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                                 rs += cf;
 #pragma unroll
                                 for (int c = 0; c < 16; ++c) {
-                                    const float4 z = *reinterpret_cast<const float4*>(sm + SM_AUX + f32_off(jr, e.half * 16 + c));
+                                    const float4 z = *reinterpret_cast<const float4*>(sm + SM_Z + f32_off(jr, e.half * 16 + c));
                                     xv[c * 4] = fmaf(cf, z.x, xv[c * 4]), xv[c * 4 + 1] = fmaf(cf, z.y, xv[c * 4 + 1]);
                                     xv[c * 4 + 2] = fmaf(cf, z.z, xv[c * 4 + 2]), xv[c * 4 + 3] = fmaf(cf, z.w, xv[c * 4 + 3]);
                                 }
@@ -857,7 +837,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                     uint4 pk;
                     pk.x = pack_bf16(xv[c * 8 + 0], xv[c * 8 + 1]), pk.y = pack_bf16(xv[c * 8 + 2], xv[c * 8 + 3]);
                     pk.z = pack_bf16(xv[c * 8 + 4], xv[c * 8 + 5]), pk.w = pack_bf16(xv[c * 8 + 6], xv[c * 8 + 7]);
-                    *reinterpret_cast<uint4*>(sm + SM_ATILE + tile_off_bf16(e.row, e.half * 64 + c * 8)) = pk;
+                    *reinterpret_cast<uint4*>(sm + SM_A1 + tile_off_bf16(e.row, e.half * 64 + c * 8)) = pk;
                 }
                 pair_sync(e.warp);                         // the row sum written by the partner thread (half 0)
                 warp_arrive(&bars[B_AREADY], lane);
@@ -892,7 +872,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                               m2 = __uint_as_float(acc[c4 * 4 + 2]) + bm.z, m3 = __uint_as_float(acc[c4 * 4 + 3]) + bm.w;
                         if (KIND == KASF_KIND_GRAPH) {
                             const float4 bv = *reinterpret_cast<const float4*>(vec + V_BV + col);
-                            const float4 z = *reinterpret_cast<const float4*>(sm + SM_AUX + f32_off(e.row, col >> 2));
+                            const float4 z = *reinterpret_cast<const float4*>(sm + SM_Z + f32_off(e.row, col >> 2));
                             m0 = fmaxf(z.x + ((m0 + rs * bv.x) * bn_s + bn_t), 0.f);
                             m1 = fmaxf(z.y + ((m1 + rs * bv.y) * bn_s + bn_t), 0.f);
                             m2 = fmaxf(z.z + ((m2 + rs * bv.z) * bn_s + bn_t), 0.f);
@@ -910,7 +890,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
             }
             PMARK(9);
             ln_stats(sm, e, xv, mean, rstd);
-            ln_write<false>(sm, e, xv, mean, rstd, vec + V_N2W, vec + V_N2B, row_ok);
+            ln_write<false>(sm, SM_A0, e, xv, mean, rstd, vec + V_N2W, vec + V_N2B, row_ok);
             tmem_st_wait();
             warp_arrive(&bars[B_AREADY], lane);
             PMARK(10);
@@ -930,7 +910,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 // while the MUFU results of group g are in flight (the compiler's own schedule consumed each result
                 // a few instructions after issuing it: 1960 vs 1440 cycles per chunk, scripts/micro/gelu_epi.cu)
                 const float* b1 = vec + V_B1 + c * 128 + e.half * 64;
-                uint8_t* hs = sm + SM_AUX + buf * TILE_BYTES;
+                uint8_t* hs = sm + SM_HS + buf * TILE_BYTES;
                 float v[2][8], w[2][8];
                 auto stage1 = [&](int g, int s2) {
                     const float4 ba = *reinterpret_cast<const float4*>(b1 + g * 8);
@@ -963,6 +943,9 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
             outb.wait();
             tc_fence_after();
             PMARK(11);
+            // ---- B1|B2 are free: request the next tile's rows; they land while the output epilogue runs
+            if (tile + (int)gridDim.x < p.ntiles)
+                gather_rows<MODE>(p, sm, tile + (int)gridDim.x, first_src, &bars[B_ROWS], warp, lane);
             // ---- out = x1 + ls2 * (acc + b2): 256-bit stores of this thread's 64 columns, straight from registers
             {
                 float* orow = p.out + (tok >= 0 ? tok : 0) * D + e.half * 64;
