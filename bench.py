@@ -181,6 +181,7 @@ def run_ours(args):
 
     timers = [_capi.LaunchTimer(cfg, B) for _ in range(args.steps)]
     n_launch = _capi.forward_launches(cfg, B)
+    n_marks = _capi.forward_marks(cfg, B)
 
     def step(timer):
         _capi.forward_into(cfg, blob, x, y, timer)
@@ -201,7 +202,7 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     # per-launch device times, averaged over the timed steps
-    per_launch = [0.0] * n_launch
+    per_launch = [0.0] * n_marks
     for tm in timers:
         for i, v in enumerate(tm.launch_ms()):
             per_launch[i] += v / args.steps

@@ -91,9 +91,13 @@ int    kasf_forward(const kasf_config* cfg, const void* packed_dev, const float*
                     void* stream);
 /* Number of kernel launches one kasf_forward(B) enqueues (for bench accounting). */
 int    kasf_forward_launches(const kasf_config* cfg, int B);
-/* Same forward, additionally recording events[0] before the first launch and events[i] after the
- * i-th launch on `stream` (n_events >= launches + 1), so a caller can read per-kernel device times
- * of the very launches it is timing.  Launch order per pass: features, then per layer att_s, att_t,
+/* Number of timing marks of kasf_forward_timed: one per stage (features, every FormerModule, every fusion,
+ * head).  Equal to the launch count for n_frames <= 128; for longer sequences a temporal module is 2-3
+ * kernels behind one mark. */
+int    kasf_forward_marks(const kasf_config* cfg, int B);
+/* Same forward, additionally recording events[0] before the first stage and events[i] after the
+ * i-th stage on `stream` (n_events >= marks + 1), so a caller can read per-stage device times
+ * of the very launches it is timing.  Stage order per pass: features, then per layer att_s, att_t,
  * graph_s, graph_t, bone_s, bone_t, fusion, and finally head.  Events come from kasf_event_create. */
 int    kasf_forward_timed(const kasf_config* cfg, const void* packed_dev, const float* x_dev,
                           float* y_dev, float* rep_dev, int B, void* ws_dev, size_t ws_bytes,
@@ -118,11 +122,20 @@ int kasf_kinematic_features(const kasf_config* cfg, const void* packed_dev, cons
 int kasf_former_module(const kasf_config* cfg, const void* packed_dev, int layer, int kind,
                        int mode, const float* in_dev, const float* XL_dev, float* out_dev, int B,
                        void* stream);
+/* Same with caller-provided scratch.  Temporal modules of sequences longer than one 128-row tile
+ * (n_frames > 128, e.g. the T=243 configs) run as a projection kernel, a per-sequence mixer-core kernel
+ * and the fused tail, exchanging bf16 Q/K/V (or A_hat z) through `scratch_dev`
+ * (>= kasf_module_scratch_bytes(cfg, B) bytes, 256-byte aligned; 0 bytes needed for n_frames <= 128,
+ * then identical to kasf_former_module).  kasf_former_module returns KASF_ENOMEM in that case. */
+size_t kasf_module_scratch_bytes(const kasf_config* cfg, int B);
+int kasf_former_module_ws(const kasf_config* cfg, const void* packed_dev, int layer, int kind,
+                          int mode, const float* in_dev, const float* XL_dev, float* out_dev, int B,
+                          void* scratch_dev, size_t scratch_bytes, void* stream);
 
 /* Profiling hook: same launch, additionally accumulating (atomicAdd by thread 0 of every CTA) the SM cycles
  * spent in each phase of the kernel into phase_cycles_dev[16] (caller zeroes it): 0 limb K/V, 1 load+LN1,
  * 2 QKV MMA wait, 3 Q/K/V drain, 4 attention core, 5 projection MMA wait, 6 similarity/top-k, 7 aggregation,
- * 8 V MMA wait, 9 mixer epilogue, 10 LN2, 11 MLP, 12 output epilogue, 13 store. */
+ * 8 V MMA wait, 9 mixer epilogue, 10 LN2, 11 MLP, 12 output epilogue, 13 wait for the gathered rows. */
 int kasf_former_module_profiled(const kasf_config* cfg, const void* packed_dev, int layer, int kind,
                                 int mode, const float* in_dev, const float* XL_dev, float* out_dev,
                                 int B, void* stream, unsigned long long* phase_cycles_dev);

@@ -49,6 +49,11 @@ _SIGNATURES = {
     "kasf_forward": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "kasf_forward_launches": (C.c_int, [C.POINTER(KasfConfig), C.c_int]),
+    "kasf_forward_marks": (C.c_int, [C.POINTER(KasfConfig), C.c_int]),
+    "kasf_module_scratch_bytes": (C.c_size_t, [C.POINTER(KasfConfig), C.c_int]),
+    "kasf_former_module_ws": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t,
+                                        C.c_void_p]),
     "kasf_forward_timed": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p), C.c_int]),
     "kasf_event_create": (C.c_void_p, []),
@@ -207,10 +212,11 @@ def forward(cfg: dict, blob: torch.Tensor, x: torch.Tensor, return_rep: bool = F
 
 
 class LaunchTimer:
-    """Per-launch CUDA events for `forward(..., timer=...)`: device time of every kernel of a forward."""
+    """Per-stage CUDA events for `forward(..., timer=...)`: device time of every stage (features, each
+    FormerModule, each fusion, head) of a forward; one stage = one kernel for n_frames <= 128."""
 
     def __init__(self, cfg: dict, B: int):
-        self.n = lib().kasf_forward_launches(C.byref(c_config(cfg)), B) + 1
+        self.n = lib().kasf_forward_marks(C.byref(c_config(cfg)), B) + 1
         self.events = (C.c_void_p * self.n)(*[lib().kasf_event_create() for _ in range(self.n)])
 
     def launch_ms(self):
@@ -241,6 +247,10 @@ def forward_launches(cfg: dict, B: int) -> int:
     return lib().kasf_forward_launches(C.byref(c_config(cfg)), B)
 
 
+def forward_marks(cfg: dict, B: int) -> int:
+    return lib().kasf_forward_marks(C.byref(c_config(cfg)), B)
+
+
 def kinematic_features(cfg, blob, x, want_raw=True):
     _require_device(x.device)
     B, T = x.shape[:2]
@@ -259,8 +269,11 @@ def former_module(cfg, blob, layer, kind, mode, v, XL=None, out=None):
     B = v.shape[0]
     out = torch.empty_like(v) if out is None else out
     with torch.cuda.device(v.device):
-        _check(lib().kasf_former_module(C.byref(c_config(cfg)), _ptr(blob), layer, KIND[kind], MODE[mode],
-                                        _ptr(v), _ptr(XL), _ptr(out), B, _stream()), "kasf_former_module")
+        nscr = lib().kasf_module_scratch_bytes(C.byref(c_config(cfg)), B) if mode == "temporal" else 0
+        scr = torch.empty(max(nscr, 256), dtype=torch.uint8, device=v.device)
+        _check(lib().kasf_former_module_ws(C.byref(c_config(cfg)), _ptr(blob), layer, KIND[kind], MODE[mode],
+                                           _ptr(v), _ptr(XL), _ptr(out), B, _ptr(scr), nscr, _stream()),
+               "kasf_former_module_ws")
     return out
 
 

@@ -99,15 +99,30 @@ int kasf_pack_weights(const kasf_config* cfg, const float* image_dev, void* pack
 
 size_t kasf_workspace_bytes(const kasf_config* cfg, int B) {
     if (config_ok(cfg) || B <= 0) return 0;
-    const long long tokens = (long long)clip_chunk(cfg, B) * cfg->n_frames * J;
-    return 6 * (((size_t)tokens * D * 4 + 1023) / 1024 * 1024);
+    const int chunk = clip_chunk(cfg, B);
+    const long long tokens = (long long)chunk * cfg->n_frames * J;
+    return 6 * (((size_t)tokens * D * 4 + 1023) / 1024 * 1024) + module_scratch_bytes(chunk, cfg->n_frames);
+}
+
+size_t kasf_module_scratch_bytes(const kasf_config* cfg, int B) {
+    if (config_ok(cfg) || B <= 0) return 0;
+    return module_scratch_bytes(B, cfg->n_frames);
+}
+
+int kasf_forward_marks(const kasf_config* cfg, int B) {
+    if (config_ok(cfg) || B <= 0) return 0;
+    const int chunk = clip_chunk(cfg, B);
+    const int passes = (B + chunk - 1) / chunk;
+    return passes * (1 + cfg->n_layers * 7 + 1);
 }
 
 int kasf_forward_launches(const kasf_config* cfg, int B) {
     if (config_ok(cfg) || B <= 0) return 0;
     const int chunk = clip_chunk(cfg, B);
     const int passes = (B + chunk - 1) / chunk;
-    return passes * (1 + cfg->n_layers * 7 + 1);
+    // T > 128: a temporal module is 3 kernels (attention, bone) or 2 (graph) instead of 1
+    const int per_layer = cfg->n_frames > 128 ? 7 + 2 + 1 + 2 : 7;
+    return passes * (1 + cfg->n_layers * per_layer + 1);
 }
 
 int kasf_kinematic_features(const kasf_config* cfg, const void* packed_dev, const float* x_dev, float* bone_dev,
@@ -120,14 +135,20 @@ int kasf_kinematic_features(const kasf_config* cfg, const void* packed_dev, cons
                            (long long)B * cfg->n_frames, (cudaStream_t)stream);
 }
 
-int kasf_former_module(const kasf_config* cfg, const void* packed_dev, int layer, int kind, int mode,
-                       const float* in_dev, const float* XL_dev, float* out_dev, int B, void* stream) {
+int kasf_former_module_ws(const kasf_config* cfg, const void* packed_dev, int layer, int kind, int mode,
+                          const float* in_dev, const float* XL_dev, float* out_dev, int B, void* scratch_dev,
+                          size_t scratch_bytes, void* stream) {
     int rc = config_ok(cfg);
     if (rc) return rc;
     if (!packed_dev || !in_dev || !out_dev || B < 0 || layer < 0 || layer >= cfg->n_layers) return KASF_EINVAL;
     if ((rc = device_ok())) return rc;
     return launch_former_module((const uint8_t*)packed_dev, layer, kind, mode, in_dev, XL_dev, out_dev, B,
-                                cfg->n_frames, (cudaStream_t)stream);
+                                cfg->n_frames, (cudaStream_t)stream, nullptr, scratch_dev, scratch_bytes);
+}
+
+int kasf_former_module(const kasf_config* cfg, const void* packed_dev, int layer, int kind, int mode,
+                       const float* in_dev, const float* XL_dev, float* out_dev, int B, void* stream) {
+    return kasf_former_module_ws(cfg, packed_dev, layer, kind, mode, in_dev, XL_dev, out_dev, B, nullptr, 0, stream);
 }
 
 int kasf_former_module_profiled(const kasf_config* cfg, const void* packed_dev, int layer, int kind, int mode,
@@ -182,6 +203,9 @@ static int forward_impl(const kasf_config* cfg, const void* packed_dev, const fl
         const int nb = B - b0 < chunk ? B - b0 : chunk;
         const long long tokens = (long long)nb * T * J;
         Streams s = carve(ws_dev, (long long)chunk * T * J);
+        const size_t stream_bytes = ((size_t)chunk * T * J * D * 4 + 1023) / 1024 * 1024;
+        void* scr = static_cast<uint8_t*>(ws_dev) + 6 * stream_bytes;     // temporal modules, T > 128 only
+        const size_t scr_bytes = module_scratch_bytes(chunk, T);
         const float* x = x_dev + (size_t)b0 * T * J * 3;
         if ((rc = launch_features(blob, x, nullptr, nullptr, s.X, s.XB, s.XL, (long long)nb * T, st))) return rc;
         KASF_MARK();
@@ -190,15 +214,15 @@ static int forward_impl(const kasf_config* cfg, const void* packed_dev, const fl
             const float* bone_src = l == 0 ? s.XB : s.X;
             if ((rc = launch_former_module(blob, l, KASF_KIND_ATTENTION, KASF_MODE_SPATIAL, s.X, nullptr, s.A, nb, T, st))) return rc;
             KASF_MARK();
-            if ((rc = launch_former_module(blob, l, KASF_KIND_ATTENTION, KASF_MODE_TEMPORAL, s.A, nullptr, s.A, nb, T, st))) return rc;
+            if ((rc = launch_former_module(blob, l, KASF_KIND_ATTENTION, KASF_MODE_TEMPORAL, s.A, nullptr, s.A, nb, T, st, nullptr, scr, scr_bytes))) return rc;
             KASF_MARK();
             if ((rc = launch_former_module(blob, l, KASF_KIND_GRAPH, KASF_MODE_SPATIAL, s.X, nullptr, s.G, nb, T, st))) return rc;
             KASF_MARK();
-            if ((rc = launch_former_module(blob, l, KASF_KIND_GRAPH, KASF_MODE_TEMPORAL, s.G, nullptr, s.G, nb, T, st))) return rc;
+            if ((rc = launch_former_module(blob, l, KASF_KIND_GRAPH, KASF_MODE_TEMPORAL, s.G, nullptr, s.G, nb, T, st, nullptr, scr, scr_bytes))) return rc;
             KASF_MARK();
             if ((rc = launch_former_module(blob, l, KASF_KIND_BONE, KASF_MODE_SPATIAL, bone_src, s.XL, s.Bn, nb, T, st))) return rc;
             KASF_MARK();
-            if ((rc = launch_former_module(blob, l, KASF_KIND_BONE, KASF_MODE_TEMPORAL, s.Bn, s.XL, s.Bn, nb, T, st))) return rc;
+            if ((rc = launch_former_module(blob, l, KASF_KIND_BONE, KASF_MODE_TEMPORAL, s.Bn, s.XL, s.Bn, nb, T, st, nullptr, scr, scr_bytes))) return rc;
             KASF_MARK();
             if ((rc = launch_fusion(blob, l, s.A, s.G, s.Bn, s.X, tokens, st))) return rc;
             KASF_MARK();
@@ -220,7 +244,7 @@ int kasf_forward(const kasf_config* cfg, const void* packed_dev, const float* x_
 int kasf_forward_timed(const kasf_config* cfg, const void* packed_dev, const float* x_dev, float* y_dev,
                        float* rep_dev, int B, void* ws_dev, size_t ws_bytes, void* stream, void** events,
                        int n_events) {
-    if (!events || n_events < kasf_forward_launches(cfg, B) + 1) return KASF_EINVAL;
+    if (!events || n_events < kasf_forward_marks(cfg, B) + 1) return KASF_EINVAL;
     return forward_impl(cfg, packed_dev, x_dev, y_dev, rep_dev, B, ws_dev, ws_bytes, stream, events);
 }
 

@@ -22,8 +22,11 @@ int launch_features(const uint8_t* blob, const float* x, float* bone, float* lim
 int launch_head(const uint8_t* blob, const float* X, float* y, float* rep, long long tokens, cudaStream_t st);
 int launch_fusion(const uint8_t* blob, int layer, const float* a, const float* g, const float* b, float* out,
                   long long tokens, cudaStream_t st);
+// `scratch` (module_scratch_bytes(B, T) bytes, 256-byte aligned) is needed by temporal modules with T > 128 only
 int launch_former_module(const uint8_t* blob, int layer, int kind, int mode, const float* in, const float* XL,
-                         float* out, int B, int T, cudaStream_t st, unsigned long long* prof = nullptr);
+                         float* out, int B, int T, cudaStream_t st, unsigned long long* prof = nullptr,
+                         void* scratch = nullptr, size_t scratch_bytes = 0);
+size_t module_scratch_bytes(int B, int T);
 int launch_metrics(int T, const float* pred, const float* pred_flip, const float* gt, const float* res,
                    const float* factor, const int32_t* action, int n_actions, double* sums, double* per_frame,
                    int B, cudaStream_t st);

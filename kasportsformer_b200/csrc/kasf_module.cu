@@ -87,7 +87,14 @@ struct ModParams {
     int ntiles;
     int groups_per_tile;     // temporal: sequences per tile
     unsigned long long* prof;   // optional [16] per-phase cycle counters (debug/profiling hook), else null
+    // long sequences (T > 128, split path): scratch in (sequence, frame) row order, row = seq * T + t
+    __nv_bfloat16* sq;       // [B*17*T, 128] Q, then the attention output O (in place) | GCN: A_hat z
+    __nv_bfloat16* sk;       // [B*17*T, 128] K
+    __nv_bfloat16* sv;       // [B*17*T, 128] V
+    float* srow;             // [B*17*T] GCN: row sums of A_hat
 };
+// internal row mapping of the split path: a tile is 128 consecutive rows of the (sequence, frame) order
+#define KASF_MODE_LONG 2
 
 __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 // the two warps (w, w+4) that share the rows of one TMEM lane quarter
@@ -138,6 +145,12 @@ __device__ __forceinline__ long long row_token(const ModParams& p, int tile, int
         if (r >= 119) return -1;
         const long long tok = (long long)tile * 119 + r;
         return tok < (long long)p.B * p.T * J ? tok : -1;
+    } else if (MODE == KASF_MODE_LONG) {
+        const long long R = (long long)tile * 128 + r;
+        if (R >= (long long)p.B * J * p.T) return -1;
+        const long long seq = R / p.T;
+        const int t = (int)(R - seq * p.T);
+        return ((seq / J) * p.T + t) * J + seq % J;
     } else {
         const int g = r / p.T;
         if (g >= p.groups_per_tile) return -1;
@@ -497,6 +510,9 @@ __device__ __forceinline__ int tile_rows(const ModParams& p, int tile) {
     if (MODE == KASF_MODE_SPATIAL) {
         const long long left = (long long)p.B * p.T * J - (long long)tile * 119;
         return (int)(left < 119 ? left : 119);
+    } else if (MODE == KASF_MODE_LONG) {
+        const long long left = (long long)p.B * J * p.T - (long long)tile * 128;
+        return (int)(left < 128 ? left : 128);
     } else {
         const long long left = (long long)p.B * J - (long long)tile * p.groups_per_tile;
         return (int)(left < p.groups_per_tile ? left : p.groups_per_tile) * p.T;
@@ -558,8 +574,12 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
 // The compute warps never issue an MMA and (apart from the mixer cores, which exchange rows through shared
 // memory) never meet at a CTA barrier: every hand-over is an mbarrier, so warps drift apart and the MUFU-bound
 // GELU epilogues of one warp overlap the tensor-memory loads, stores and MMAs triggered by the others.
+// MODE == KASF_MODE_LONG is the tail of the split path for sequences longer than a tile (T > 128): the mixer
+// core ran in its own kernels (kasf_long section below) and left the attention output / A_hat z in scratch;
+// this kernel then does projection -> residual -> LN2 -> MLP -> residual on plain 128-row tiles.
 template <int KIND, int MODE, int TC>
 __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const ModParams p) {
+    constexpr bool POST = MODE == KASF_MODE_LONG;
     extern __shared__ __align__(1024) uint8_t sm[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM_BARS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + SM_BARS + B_COUNT * 8);
@@ -587,12 +607,13 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
     const uint32_t tmem = *tmem_slot;
 
     // chunk consumption order (indices into the module's 12 chunks; see kasf_layout.h)
-    constexpr int NCH = KIND == KASF_KIND_GRAPH ? 10 : 12;
+    constexpr int NCH = KIND == KASF_KIND_GRAPH ? 10 : (POST ? 9 : 12);
+    constexpr int ORD_POST[12] = {3, 4, 5, 6, 8, 7, 9, 10, 11, 0, 0, 0};   // attention / bone tail: projection + MLP
     //                         mixer chunks                         MLP: W1_0 W1_1 W1_2 W2_0 W1_3 W2_1 W2_2 W2_3
     constexpr int ORD_ATT[12] = {0, 1, 2, 3, 4, 5, 6, 8, 7, 9, 10, 11};
     constexpr int ORD_BONE[12] = {1, 2, 0, 3, 4, 5, 6, 8, 7, 9, 10, 11};
     constexpr int ORD_GCN[12] = {0, 1, 4, 5, 6, 8, 7, 9, 10, 11, 0, 0};
-    const float* first_src = KIND == KASF_KIND_BONE ? p.xl : p.in;
+    const float* first_src = (KIND == KASF_KIND_BONE && !POST) ? p.xl : p.in;
 
     if (warp >= CW) {
         // ===================== service warpgroup (hands its registers to the compute warpgroups) =====================
@@ -604,7 +625,8 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
 #pragma unroll 1
                     for (int i = 0; i < NCH; ++i) {
-                        const int ci = KIND == KASF_KIND_ATTENTION ? ORD_ATT[i] : (KIND == KASF_KIND_BONE ? ORD_BONE[i] : ORD_GCN[i]);
+                        const int ci = KIND == KASF_KIND_GRAPH ? ORD_GCN[i]
+                                       : (POST ? ORD_POST[i] : (KIND == KASF_KIND_ATTENTION ? ORD_ATT[i] : ORD_BONE[i]));
                         mbar_wait_suspend(&bars[B_EMPTY0 + slot], ph ^ 1);
                         mbar_arrive_expect_tx(&bars[B_FULL0 + slot], CHUNK_BYTES);
                         bulk_g2s(sm + SM_RING + slot * CHUNK_BYTES, chunks + (size_t)ci * CHUNK_BYTES, CHUNK_BYTES,
@@ -631,7 +653,9 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 tc_fence_after();
             };
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                if (KIND == KASF_KIND_ATTENTION) {
+                if (POST && KIND != KASF_KIND_GRAPH) {
+                    // Q, K, V were projected by the pre kernel
+                } else if (KIND == KASF_KIND_ATTENTION) {
                     wait_a();                                  // LN1(x)
                     chunk(TM_MIX, a1_addr, false);             // Q
                     chunk(TM_K, a1_addr, false);
@@ -706,7 +730,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
             float xv[64];
             float mean, rstd;
 
-            if (KIND == KASF_KIND_BONE) {
+            if (KIND == KASF_KIND_BONE && !POST) {
                 // ---- K,V from the limb stream: LN_limb(XL) Wkv^T
                 rows.wait();
                 read_staged(sm, e, xv, row_ok);
@@ -728,18 +752,32 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 for (int i = 0; i < 32; ++i) xr[i] = __float_as_uint(xv[b * 32 + i]);
                 tmem_st32(e.tbase + TM_X + e.half * 64 + b * 32, xr);
             }
-            ln_stats(sm, e, xv, mean, rstd);
-            if (KIND == KASF_KIND_BONE) {
-                mma.wait();                                // K,V complete: the A tile may be overwritten
-                tc_fence_after();
+            if (POST && KIND != KASF_KIND_GRAPH) {
+                // ---- split path: the attention output of this tile's rows (bf16, scratch) is the A operand
+                const uint4* src = reinterpret_cast<const uint4*>(p.sq + ((long long)tile * 128 + e.row) * D + e.half * 64);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint4 o8 = row_ok ? __ldg(src + c) : make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4*>(sm + SM_A0 + tile_off_bf16(e.row, e.half * 64 + c * 8)) = o8;
+                }
+            } else {
+                ln_stats(sm, e, xv, mean, rstd);
+                if (KIND == KASF_KIND_BONE) {
+                    mma.wait();                            // K,V complete: the A tile may be overwritten
+                    tc_fence_after();
+                }
+                if (KIND == KASF_KIND_GRAPH) csync();      // z (fp32) overwrites the staging rows of other threads
+                ln_write<KIND == KASF_KIND_GRAPH>(sm, SM_A1, e, xv, mean, rstd, vec + V_N1W, vec + V_N1B, row_ok);
             }
-            if (KIND == KASF_KIND_GRAPH) csync();          // z (fp32) overwrites the staging rows of other threads
-            ln_write<KIND == KASF_KIND_GRAPH>(sm, SM_A1, e, xv, mean, rstd, vec + V_N1W, vec + V_N1B, row_ok);
             tmem_st_wait();
             warp_arrive(&bars[B_AREADY], lane);
             PMARK(1);
 
-            if (KIND != KASF_KIND_GRAPH) {
+            if (KIND != KASF_KIND_GRAPH && POST) {
+                mma.wait();                                // output projection
+                tc_fence_after();
+                PMARK(5);
+            } else if (KIND != KASF_KIND_GRAPH) {
                 mma.wait();                                // Q (and K,V) in tensor memory
                 tc_fence_after();
                 PMARK(2);
@@ -777,7 +815,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 PMARK(5);
             } else {
                 // ================= GCN mixer =================
-                csync();                                   // z of the whole tile is in AUX
+                if (!POST) csync();                        // z of the whole tile is in shared memory
                 if (MODE == KASF_MODE_TEMPORAL) {
                     similarity_topk<TC>(sm, warp, lane, p.T, nrows);
                     csync();
@@ -785,9 +823,17 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 }
                 // ---- aggregation  agg_i = sum_j A_ij / sqrt(d_i d_j) * z_j : this thread's 64 columns of its row
                 float rs = 0.f;
+                uint4 agg8[8];                             // split path: A_hat z of this row (bf16) from scratch
+                if (POST) {
+                    const long long R = (long long)tile * 128 + e.row;
+                    const uint4* src = reinterpret_cast<const uint4*>(p.sq + R * D + e.half * 64);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) agg8[c] = row_ok ? __ldg(src + c) : make_uint4(0u, 0u, 0u, 0u);
+                    rs = row_ok ? __ldg(p.srow + R) : 0.f;
+                }
 #pragma unroll
                 for (int i = 0; i < 64; ++i) xv[i] = 0.f;
-                if (row_ok) {
+                if (row_ok && !POST) {
                     if (MODE == KASF_MODE_SPATIAL) {
                         const int j = e.row % J, base = e.row - j;
                         const float di = c_rsd[c_deg[j]];
@@ -835,8 +881,12 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     uint4 pk;
-                    pk.x = pack_bf16(xv[c * 8 + 0], xv[c * 8 + 1]), pk.y = pack_bf16(xv[c * 8 + 2], xv[c * 8 + 3]);
-                    pk.z = pack_bf16(xv[c * 8 + 4], xv[c * 8 + 5]), pk.w = pack_bf16(xv[c * 8 + 6], xv[c * 8 + 7]);
+                    if (POST) {
+                        pk = agg8[c];
+                    } else {
+                        pk.x = pack_bf16(xv[c * 8 + 0], xv[c * 8 + 1]), pk.y = pack_bf16(xv[c * 8 + 2], xv[c * 8 + 3]);
+                        pk.z = pack_bf16(xv[c * 8 + 4], xv[c * 8 + 5]), pk.w = pack_bf16(xv[c * 8 + 6], xv[c * 8 + 7]);
+                    }
                     *reinterpret_cast<uint4*>(sm + SM_A1 + tile_off_bf16(e.row, e.half * 64 + c * 8)) = pk;
                 }
                 pair_sync(e.warp);                         // the row sum written by the partner thread (half 0)
@@ -852,7 +902,8 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 // GCN: mix = relu(z + BN_node(acc + bU + rowsum*bV)); others: mix = acc + bproj
                 float bn_s = 1.f, bn_t = 0.f, rs = 0.f;
                 if (KIND == KASF_KIND_GRAPH) {
-                    const int node = MODE == KASF_MODE_SPATIAL ? e.row % J : e.row % p.T;
+                    const int node = MODE == KASF_MODE_SPATIAL ? e.row % J
+                                     : (POST ? (int)(((long long)tile * 128 + e.row) % p.T) : e.row % p.T);
                     bn_s = vec[V_BNS + node];
                     bn_t = vec[V_BNT + node];
                     rs = *reinterpret_cast<const float*>(sm + SM_ROWSUM + e.row * 4);
@@ -991,13 +1042,456 @@ static int launch_one(const ModParams& p, cudaStream_t st) {
     return cuda_status();
 }
 
+// ============================================================================================== split path (T > 128)
+// A temporal sequence longer than one 128-row tile (T = 243) does not fit the fused kernel's "a tile owns whole
+// groups" scheme, so the module runs as three kernels over scratch in (sequence, frame) row order:
+//   attention / bone:  long_pre_kernel (LN1 [, LN_limb] -> Q, K, V on tcgen05 -> bf16 scratch)
+//                      long_attention_kernel (one CTA per sequence: softmax(q k^T / 4) v, Q|K|V resident in smem)
+//                      former_module_kernel<KIND, KASF_MODE_LONG> (projection, residual, LN2, MLP, residual)
+//   graph:             long_gcn_kernel (one CTA per sequence: z = LN1(x) fp32 in smem, 3xTF32 similarity, exact
+//                      4th-largest threshold, degrees, A_hat z and row sums -> scratch)
+//                      former_module_kernel<GRAPH, KASF_MODE_LONG> (U z + (A_hat z) V^T, BN, residuals, MLP)
+// Same arithmetic as the fused kernels (bf16 operands, fp32 accumulation / statistics / softmax / similarity).
+
+// ---- Q, K, V projection of 128 consecutive (sequence, frame) rows.  One CTA per tile, 8 warps, thread = half a
+//      row; the three weight chunks land in the ring region with one bulk copy each.
+template <int KIND>
+__global__ void __launch_bounds__(256, 1) long_pre_kernel(const ModParams p) {
+    extern __shared__ __align__(1024) uint8_t sm[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM_BARS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + SM_BARS + 64);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, tile = blockIdx.x;
+    const float* vec = reinterpret_cast<const float*>(sm + SM_VEC);
+    const uint8_t* chunks = p.mod + MOD_VEC_BYTES;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+        // ring slot i <- chunk ORD[i]: attention Q,K,V = 0,1,2; bone K,V,Q = 1,2,0
+        mbar_arrive_expect_tx(&bars[0], 3 * CHUNK_BYTES);
+        for (int i = 0; i < 3; ++i) {
+            const int ci = KIND == KASF_KIND_ATTENTION ? i : (i + 1) % 3;
+            bulk_g2s(sm + SM_RING + i * CHUNK_BYTES, chunks + (size_t)ci * CHUNK_BYTES, CHUNK_BYTES, &bars[0]);
+        }
+    }
+    if (warp == 0) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    for (int i = tid; i < V_FLOATS / 4; i += 256) reinterpret_cast<float4*>(sm + SM_VEC)[i] = reinterpret_cast<const float4*>(p.mod)[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    EpiMap e;
+    e.row = (warp & 3) * 32 + lane, e.half = warp >> 2, e.warp = warp;
+    e.tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const int nrows = tile_rows<KASF_MODE_LONG>(p, tile);
+    const bool row_ok = e.row < nrows;
+    const long long tok = row_ok ? row_token<KASF_MODE_LONG>(p, tile, e.row) : 0;
+    const uint32_t a_addr = smem_u32(sm + SM_A0), ring = smem_u32(sm + SM_RING);
+    float xv[64], mean, rstd;
+    auto load_row = [&](const float* src) {
+        if (row_ok) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) ldg256(src + tok * D + e.half * 64 + c * 8, xv + c * 8);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) xv[i] = 0.f;
+        }
+    };
+    uint32_t ph = 0;
+    if (KIND == KASF_KIND_BONE) {
+        load_row(p.xl);
+        ln_stats(sm, e, xv, mean, rstd);
+        ln_write<false>(sm, SM_A0, e, xv, mean, rstd, vec + V_NLW, vec + V_NLB, row_ok);
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            mbar_wait(&bars[0], 0);
+            tc_fence_after();
+            umma_tile_k128(tmem + TM_K, a_addr, ring, 128, false);
+            umma_tile_k128(tmem + TM_V, a_addr, ring + CHUNK_BYTES, 128, false);
+            tc_commit(&bars[1]);
+        }
+        mbar_wait(&bars[1], ph);
+        ph ^= 1;
+        tc_fence_after();
+    }
+    load_row(p.in);
+    ln_stats(sm, e, xv, mean, rstd);
+    ln_write<false>(sm, SM_A0, e, xv, mean, rstd, vec + V_N1W, vec + V_N1B, row_ok);
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+        mbar_wait(&bars[0], 0);
+        tc_fence_after();
+        if (KIND == KASF_KIND_ATTENTION) {
+            umma_tile_k128(tmem + TM_MIX, a_addr, ring, 128, false);
+            umma_tile_k128(tmem + TM_K, a_addr, ring + CHUNK_BYTES, 128, false);
+            umma_tile_k128(tmem + TM_V, a_addr, ring + 2 * CHUNK_BYTES, 128, false);
+        } else {
+            umma_tile_k128(tmem + TM_MIX, a_addr, ring + 2 * CHUNK_BYTES, 128, false);
+        }
+        tc_commit(&bars[1]);
+    }
+    mbar_wait(&bars[1], ph);
+    tc_fence_after();
+    // ---- drain: bf16 rows of Q, K, V -> scratch (128 contiguous bytes per thread and matrix)
+    const long long R = (long long)tile * 128 + e.row;
+#pragma unroll
+    for (int qkv = 0; qkv < 3; ++qkv) {
+        __nv_bfloat16* dst = (qkv == 0 ? p.sq : (qkv == 1 ? p.sk : p.sv)) + R * D + e.half * 64;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            uint32_t acc[32];
+            tmem_ld32(e.tbase + qkv * 128 + e.half * 64 + b * 32, acc);
+            tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint4 pk;
+                    pk.x = pack_bf16(__uint_as_float(acc[c * 8 + 0]), __uint_as_float(acc[c * 8 + 1]));
+                    pk.y = pack_bf16(__uint_as_float(acc[c * 8 + 2]), __uint_as_float(acc[c * 8 + 3]));
+                    pk.z = pack_bf16(__uint_as_float(acc[c * 8 + 4]), __uint_as_float(acc[c * 8 + 5]));
+                    pk.w = pack_bf16(__uint_as_float(acc[c * 8 + 6]), __uint_as_float(acc[c * 8 + 7]));
+                    *reinterpret_cast<uint4*>(dst + b * 32 + c * 8) = pk;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ---- attention core of one (clip, joint) sequence, T <= 256: Q | K | V bf16 [256 x 128] resident in shared
+//      memory (rows >= T zero), warp = head, 16-query blocks, two passes over the keys (row maximum, then
+//      probabilities and P V) so that the rounding is the one of the fused kernel; the output replaces Q.
+constexpr uint32_t LA_TILE = 256 * 256;   // one [256 rows x 128 bf16] tile
+__device__ __forceinline__ uint32_t la_off(uint32_t r, uint32_t c16) { return r * 256u + ((c16 ^ (r & 7u)) << 4); }
+
+__global__ void __launch_bounds__(256, 1) long_attention_kernel(const ModParams p) {
+    extern __shared__ __align__(1024) uint8_t sm[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, T = p.T;
+    const long long seq = blockIdx.x;
+    __nv_bfloat16* gq = p.sq + seq * T * D;
+    const __nv_bfloat16* gk = p.sk + seq * T * D;
+    const __nv_bfloat16* gv = p.sv + seq * T * D;
+    // ---- load (16-byte chunks, coalesced), zero the tail rows
+    for (int i = tid; i < 3 * 256 * 16; i += 256) {
+        const int m = i / (256 * 16), r = (i / 16) & 255, c = i & 15;
+        uint8_t* dst = sm + m * LA_TILE + la_off(r, c);
+        if (r < T) {
+            const __nv_bfloat16* src = (m == 0 ? gq : (m == 1 ? gk : gv)) + (size_t)r * D + c * 8;
+            cp_async16(dst, src, 16u);
+        } else {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+    const uint32_t qb = smem_u32(sm), kb = smem_u32(sm + LA_TILE), vb = smem_u32(sm + 2 * LA_TILE);
+    const int h = warp;
+    const int g8 = lane >> 2, t4 = lane & 3, mi = lane >> 3, r8 = lane & 7;
+    const float scale = 0.25f * 1.4426950408889634f;
+    const int mtiles = (T + 15) >> 4, nkb = (T + 63) >> 6;        // 16-query blocks, 64-key blocks
+#pragma unroll 1
+    for (int mt = 0; mt < mtiles; ++mt) {
+        uint32_t qa[4];
+        ldsm_x4(qb + la_off(mt * 16 + (mi & 1) * 8 + r8, 2 * h + (mi >> 1)), qa);
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+        auto scores = [&](int kblk, float (&s)[8][4]) {
+#pragma unroll
+            for (int nt = 0; nt < 8; nt += 2) {
+                uint32_t kf[4];
+                ldsm_x4(kb + la_off(kblk * 64 + 8 * (nt + (mi >> 1)) + r8, 2 * h + (mi & 1)), kf);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) s[nt][i] = 0.f, s[nt + 1][i] = 0.f;
+                mma_bf16_16816(s[nt], qa, kf[0], kf[1]);
+                mma_bf16_16816(s[nt + 1], qa, kf[2], kf[3]);
+            }
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (kblk * 64 + nt * 8 + t4 * 2 + (i & 1) >= T) s[nt][i] = -INFINITY;
+        };
+#pragma unroll 1
+        for (int kblk = 0; kblk < nkb; ++kblk) {                 // pass 1: row maxima
+            float s[8][4];
+            scores(kblk, s);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+                mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+            }
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float nm0 = -mx0 * scale, nm1 = -mx1 * scale;
+        float l0 = 0.f, l1 = 0.f, o[2][4];
+#pragma unroll
+        for (int dn = 0; dn < 2; ++dn)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[dn][i] = 0.f;
+#pragma unroll 1
+        for (int kblk = 0; kblk < nkb; ++kblk) {                 // pass 2: probabilities, P V
+            float s[8][4];
+            scores(kblk, s);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                s[nt][0] = ex2_approx(fmaf(s[nt][0], scale, nm0)), s[nt][1] = ex2_approx(fmaf(s[nt][1], scale, nm0));
+                s[nt][2] = ex2_approx(fmaf(s[nt][2], scale, nm1)), s[nt][3] = ex2_approx(fmaf(s[nt][3], scale, nm1));
+                l0 += s[nt][0] + s[nt][1];
+                l1 += s[nt][2] + s[nt][3];
+            }
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                uint32_t pa[4], vf[4];
+                pa[0] = pack_bf16(s[2 * ks][0], s[2 * ks][1]), pa[1] = pack_bf16(s[2 * ks][2], s[2 * ks][3]);
+                pa[2] = pack_bf16(s[2 * ks + 1][0], s[2 * ks + 1][1]), pa[3] = pack_bf16(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+                ldsm_x4_t(vb + la_off(kblk * 64 + 16 * ks + (mi & 1) * 8 + r8, 2 * h + (mi >> 1)), vf);
+                mma_bf16_16816(o[0], pa, vf[0], vf[1]);
+                mma_bf16_16816(o[1], pa, vf[2], vf[3]);
+            }
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1), l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 2), l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float i0 = rcp_approx(l0), i1 = rcp_approx(l1);
+        // the output of this (head, query block) replaces the Q block this warp alone reads
+        __syncwarp();
+#pragma unroll
+        for (int dn = 0; dn < 2; ++dn) {
+            const int r0 = mt * 16 + g8, r1 = r0 + 8;
+            *reinterpret_cast<uint32_t*>(sm + la_off(r0, 2 * h + dn) + t4 * 4) = pack_bf16(o[dn][0] * i0, o[dn][1] * i0);
+            *reinterpret_cast<uint32_t*>(sm + la_off(r1, 2 * h + dn) + t4 * 4) = pack_bf16(o[dn][2] * i1, o[dn][3] * i1);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < T * 16; i += 256) {
+        const int r = i >> 4, c = i & 15;
+        *reinterpret_cast<uint4*>(gq + (size_t)r * D + c * 8) = *reinterpret_cast<const uint4*>(sm + la_off(r, c));
+    }
+}
+
+// ---- temporal GCN adjacency + aggregation of one (clip, joint) sequence, T <= 256 (graph.py:99-134)
+constexpr uint32_t LG_Z = 0;                       // fp32 [256][128], f32_off layout
+constexpr uint32_t LG_ADJ = 256 * 512;             // u32 [256][8]
+constexpr uint32_t LG_RSD = LG_ADJ + 256 * 32;     // f32 [256]
+constexpr uint32_t LG_TOTAL = LG_RSD + 1024;
+
+__global__ void __launch_bounds__(256, 1) long_gcn_kernel(const ModParams p) {
+    extern __shared__ __align__(1024) uint8_t sm[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, T = p.T;
+    const long long seq = blockIdx.x, b = seq / J;
+    const int j = (int)(seq % J);
+    const float* vecg = reinterpret_cast<const float*>(p.mod);
+    uint32_t* adj = reinterpret_cast<uint32_t*>(sm + LG_ADJ);
+    float* rsd = reinterpret_cast<float*>(sm + LG_RSD);
+    // ---- z = LN1(x) in fp32, warp per row (lane = 4 columns), exact two-pass statistics
+    const float4 gam = *reinterpret_cast<const float4*>(vecg + V_N1W + lane * 4);
+    const float4 bet = *reinterpret_cast<const float4*>(vecg + V_N1B + lane * 4);
+    for (int r = warp; r < 256; r += 8) {
+        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < T) {
+            const float4 x = *reinterpret_cast<const float4*>(p.in + (((b * T + r) * J + j) * D) + lane * 4);
+            float s = (x.x + x.y) + (x.z + x.w);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const float mean = s * (1.0f / D);
+            const float d0 = x.x - mean, d1 = x.y - mean, d2 = x.z - mean, d3 = x.w - mean;
+            float q = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3)));
+#pragma unroll
+            for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+            const float rstd = 1.0f / sqrtf(q * (1.0f / D) + 1e-5f);
+            z.x = fmaf(d0 * rstd, gam.x, bet.x), z.y = fmaf(d1 * rstd, gam.y, bet.y);
+            z.z = fmaf(d2 * rstd, gam.z, bet.z), z.w = fmaf(d3 * rstd, gam.w, bet.w);
+        }
+        *reinterpret_cast<float4*>(sm + LG_Z + f32_off(r, lane)) = z;
+    }
+    __syncthreads();
+    // ---- similarity rows (3xTF32) and the 4th-largest threshold, 16 rows per work item
+    const int g8 = lane >> 2, t4 = lane & 3;
+    const int mtiles = (T + 15) >> 4, nkt = (T + 7) >> 3;
+#pragma unroll 1
+    for (int mt = warp; mt < mtiles; mt += 8) {
+        const int ra = mt * 16 + g8, rb = ra + 8;               // < 256: rows >= T are zero
+        float s[32][4];
+#pragma unroll
+        for (int nt = 0; nt < 32; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s[nt][i] = 0.f;
+#pragma unroll 1
+        for (int ks = 0; ks < 16; ++ks) {
+            float av[4];
+            av[0] = *reinterpret_cast<const float*>(sm + LG_Z + f32_off(ra, 2 * ks) + t4 * 4);
+            av[1] = *reinterpret_cast<const float*>(sm + LG_Z + f32_off(rb, 2 * ks) + t4 * 4);
+            av[2] = *reinterpret_cast<const float*>(sm + LG_Z + f32_off(ra, 2 * ks + 1) + t4 * 4);
+            av[3] = *reinterpret_cast<const float*>(sm + LG_Z + f32_off(rb, 2 * ks + 1) + t4 * 4);
+            uint32_t ah[4], al[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ah[i] = __float_as_uint(av[i]) & 0xffffe000u;
+                al[i] = __float_as_uint(av[i] - __uint_as_float(ah[i]));
+            }
+#pragma unroll
+            for (int nt = 0; nt < 32; ++nt) {
+                if (nt < nkt) {
+                    const int rj = 8 * nt + g8;
+                    const float b0 = *reinterpret_cast<const float*>(sm + LG_Z + f32_off(rj, 2 * ks) + t4 * 4);
+                    const float b1 = *reinterpret_cast<const float*>(sm + LG_Z + f32_off(rj, 2 * ks + 1) + t4 * 4);
+                    const uint32_t bh0 = __float_as_uint(b0) & 0xffffe000u, bh1 = __float_as_uint(b1) & 0xffffe000u;
+                    const uint32_t bl0 = __float_as_uint(b0 - __uint_as_float(bh0));
+                    const uint32_t bl1 = __float_as_uint(b1 - __uint_as_float(bh1));
+                    mma_tf32_1688(s[nt], al, bh0, bh1);
+                    mma_tf32_1688(s[nt], ah, bl0, bl1);
+                    mma_tf32_1688(s[nt], ah, bh0, bh1);
+                }
+            }
+        }
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow) {
+            // 4th largest with multiplicity (torch.topk): walk down the distinct values, counting copies
+            // (all lanes run the four rounds: the quads of a warp finish at different rounds and shuffle together)
+            float cur = INFINITY, thr = -INFINITY;
+            int rem = 4;
+            bool done = false;
+#pragma unroll 1
+            for (int it = 0; it < 4; ++it) {
+                float m = -INFINITY;
+#pragma unroll
+                for (int nt = 0; nt < 32; ++nt)
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const float v = s[nt][hrow * 2 + i];
+                        if (nt * 8 + t4 * 2 + i < T && v < cur) m = fmaxf(m, v);
+                    }
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+                int cnt = 0;
+#pragma unroll
+                for (int nt = 0; nt < 32; ++nt)
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+                        cnt += (nt * 8 + t4 * 2 + i < T && s[nt][hrow * 2 + i] == m) ? 1 : 0;
+                cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+                cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+                if (!done) {
+                    thr = m;
+                    if (cnt >= rem) done = true;
+                    rem -= cnt;
+                    cur = m;
+                }
+            }
+            const int row = mt * 16 + g8 + hrow * 8;
+            int deg = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                uint32_t bits = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int nt = w * 4 + q;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+                        if (nt * 8 + t4 * 2 + i < T && s[nt][hrow * 2 + i] >= thr) bits |= 1u << (q * 8 + t4 * 2 + i);
+                }
+                bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
+                bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
+                deg += __popc(bits);
+                if (t4 == 0 && row < T) adj[row * 8 + w] = bits;
+            }
+            if (t4 == 0 && row < T) rsd[row] = 1.0f / sqrtf((float)deg);
+        }
+    }
+    __syncthreads();
+    // ---- A_hat z (sparse gather, fp32) -> bf16 scratch; row sums of A_hat
+    for (int task = tid; task < 2 * T; task += 256) {
+        const int row = task >> 1, half = task & 1;
+        float a[64], rs = 0.f;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) a[i] = 0.f;
+        const float di = rsd[row];
+#pragma unroll 1
+        for (int w = 0; w < 8; ++w) {
+            unsigned bits = adj[row * 8 + w];
+#pragma unroll 1
+            while (bits) {
+                const int jr = 32 * w + __ffs(bits) - 1;
+                bits &= bits - 1;
+                const float cf = di * rsd[jr];
+                rs += cf;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const float4 z = *reinterpret_cast<const float4*>(sm + LG_Z + f32_off(jr, half * 16 + c));
+                    a[c * 4] = fmaf(cf, z.x, a[c * 4]), a[c * 4 + 1] = fmaf(cf, z.y, a[c * 4 + 1]);
+                    a[c * 4 + 2] = fmaf(cf, z.z, a[c * 4 + 2]), a[c * 4 + 3] = fmaf(cf, z.w, a[c * 4 + 3]);
+                }
+            }
+        }
+        const long long R = seq * T + row;
+        __nv_bfloat16* dst = p.sq + R * D + half * 64;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            uint4 pk;
+            pk.x = pack_bf16(a[c * 8 + 0], a[c * 8 + 1]), pk.y = pack_bf16(a[c * 8 + 2], a[c * 8 + 3]);
+            pk.z = pack_bf16(a[c * 8 + 4], a[c * 8 + 5]), pk.w = pack_bf16(a[c * 8 + 6], a[c * 8 + 7]);
+            *reinterpret_cast<uint4*>(dst + c * 8) = pk;
+        }
+        if (half == 0) p.srow[R] = rs;
+    }
+}
+
+size_t module_scratch_bytes(int B, int T) {
+    if (T <= 128 || B <= 0) return 0;
+    const size_t rows = (size_t)B * J * T;
+    return 3 * rows * D * 2 + ((rows * 4 + 255) / 256) * 256;
+}
+
+static int launch_long(ModParams p, int kind, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+    if (p.T > 256) return KASF_ESHAPE;
+    if (!scratch || scratch_bytes < module_scratch_bytes(p.B, p.T) || ((uintptr_t)scratch & 255) != 0) return KASF_ENOMEM;
+    const size_t rows = (size_t)p.B * J * p.T;
+    p.sq = static_cast<__nv_bfloat16*>(scratch);
+    p.sk = p.sq + rows * D;
+    p.sv = p.sk + rows * D;
+    p.srow = reinterpret_cast<float*>(p.sv + rows * D);
+    p.groups_per_tile = 0;
+    p.ntiles = (int)((rows + 127) / 128);
+    const int seqs = p.B * J;
+    int rc;
+    if (kind == KASF_KIND_GRAPH) {
+        cudaFuncSetAttribute(long_gcn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LG_TOTAL);
+        long_gcn_kernel<<<seqs, 256, LG_TOTAL, st>>>(p);
+        if ((rc = cuda_status())) return rc;
+        return launch_one<KASF_KIND_GRAPH, KASF_MODE_LONG, 0>(p, st);
+    }
+    if (kind == KASF_KIND_ATTENTION) {
+        cudaFuncSetAttribute(long_pre_kernel<KASF_KIND_ATTENTION>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+        long_pre_kernel<KASF_KIND_ATTENTION><<<p.ntiles, 256, SM_TOTAL, st>>>(p);
+    } else {
+        cudaFuncSetAttribute(long_pre_kernel<KASF_KIND_BONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+        long_pre_kernel<KASF_KIND_BONE><<<p.ntiles, 256, SM_TOTAL, st>>>(p);
+    }
+    if ((rc = cuda_status())) return rc;
+    cudaFuncSetAttribute(long_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * LA_TILE);
+    long_attention_kernel<<<seqs, 256, 3 * LA_TILE, st>>>(p);
+    if ((rc = cuda_status())) return rc;
+    return kind == KASF_KIND_ATTENTION ? launch_one<KASF_KIND_ATTENTION, KASF_MODE_LONG, 0>(p, st)
+                                       : launch_one<KASF_KIND_BONE, KASF_MODE_LONG, 0>(p, st);
+}
+
 int launch_former_module(const uint8_t* blob, int layer, int kind, int mode, const float* in, const float* XL,
-                         float* out, int B, int T, cudaStream_t st, unsigned long long* prof) {
+                         float* out, int B, int T, cudaStream_t st, unsigned long long* prof, void* scratch,
+                         size_t scratch_bytes) {
     if (B <= 0) return KASF_OK;
     if (kind < 0 || kind > 2 || mode < 0 || mode > 1) return KASF_EINVAL;
     if (kind == KASF_KIND_BONE && !XL) return KASF_EINVAL;
-    if (mode == KASF_MODE_TEMPORAL && T > 128) return KASF_ESHAPE;   // TODO: two-tile sequences (T=243)
     if ((((uintptr_t)in | (uintptr_t)out | (uintptr_t)XL) & 31) != 0) return KASF_EINVAL;   // 256-bit row accesses
+    if ((long long)B * T * J >= (1LL << 31)) return KASF_ESHAPE;                             // 32-bit token indices
     ModParams p;
     // module order in the blob: att_s, att_t, graph_s, graph_t, bone_s, bone_t
     p.mod = blob + module_off(layer, kind * 2 + mode);
@@ -1007,6 +1501,9 @@ int launch_former_module(const uint8_t* blob, int layer, int kind, int mode, con
     p.B = B;
     p.T = T;
     p.prof = prof;
+    p.sq = p.sk = p.sv = nullptr;
+    p.srow = nullptr;
+    if (mode == KASF_MODE_TEMPORAL && T > 128) return launch_long(p, kind, scratch, scratch_bytes, st);
     int tc = 0;
     if (mode == KASF_MODE_SPATIAL) {
         p.groups_per_tile = 7;

@@ -84,11 +84,12 @@ def _module_oracle(state, cfg, layer, br, kind, mode, v, XL, emulate):
 MODULES = [("att", "attention"), ("graph", "graph"), ("bone", "bone")]
 
 
-@pytest.mark.parametrize("T,B", [(27, 3), (27, 10), (9, 5), (81, 2), (128, 1), (100, 2)])
+@pytest.mark.parametrize("T,B", [(27, 3), (27, 10), (9, 5), (81, 2), (128, 1), (100, 2), (243, 1), (243, 2), (150, 2)])
 @pytest.mark.parametrize("mode", ["spatial", "temporal"])
 @pytest.mark.parametrize("br,kind", MODULES)
 def test_former_module(br, kind, mode, T, B):
-    """One fused FormerModule kernel vs the oracle.
+    """One FormerModule (the fused kernel; for temporal modules with T > 128 the split path: projection kernel,
+    per-sequence mixer-core kernel, fused tail) vs the oracle.
 
     (a) against the oracle emulating the kernel's bf16 operand rounding: update error <= 2e-3 of the
         update magnitude (accumulation order, bf16 re-rounding of aggregated rows);
