@@ -247,6 +247,18 @@ def run_ours(args):
         mod_flops = 26 * sum(2.0 * module_macs_per_token(k, m, T) * tokens for k, m in kinds)
         achieved = mod_flops / (mod_ms / 1e3) / 1e12
         step_ms = sum(per_launch)
+        # DRAM traffic of the same kernels from the committed `ncu --set full` capture (per launch, mean of the six
+        # instantiations); only valid for the configuration the capture was taken on
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            if tj["batch"] == B and tj["frames"] == T:
+                per = [v["dram_read_bytes"] + v["dram_write_bytes"] for v in tj["per_launch"].values()]
+                traffic, traffic_src = sum(per) / len(per), tj["capture"]
+        # algorithmic HBM bytes per launch: 512 B read + 512 B written per token (+ 512 B of the limb stream in the
+        # two bone modules): mean over the six instantiations
+        alg_bytes = tokens * 512 * (2 * 4 + 3 * 2) / 6
         out = {
             "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -260,7 +272,9 @@ def run_ours(args):
             "gpu_launches": (n_launch + 1) * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["bf16"], "traffic": None, "peak_source": pk["src"],
+                         "frac": achieved / pk["bf16"], "traffic": traffic, "traffic_unit": "bytes/launch (dram read+write, ncu)",
+                         "traffic_source": traffic_src, "algorithmic_bytes_per_launch": alg_bytes,
+                         "algorithmic_flops_per_launch": mod_flops / 156, "peak_source": pk["src"],
                          "kernel": "former_module_kernel<KIND,MODE> (6 instantiations, 156 launches/forward)",
                          "share_of_step": mod_ms / step_ms,
                          "per_kind_ms_per_forward": {k: round(v, 4) for k, v in per_kind_ms.items()},
