@@ -132,7 +132,11 @@ struct WaitBar {
     uint64_t* bar;
     uint32_t phase;
     __device__ __forceinline__ void wait() {
+#ifdef KASF_SUSPEND_WAITS
+        mbar_wait_suspend(bar, phase);
+#else
         mbar_wait(bar, phase);
+#endif
         phase ^= 1;
     }
 };
