@@ -279,7 +279,7 @@ def former_module(cfg, blob, layer, kind, mode, v, XL=None, out=None):
 
 PHASES = ["limb_kv", "load_ln1", "qkv_mma_wait", "qkv_drain", "attention", "proj_mma_wait", "similarity",
           "aggregation", "v_mma_wait", "mixer_epilogue", "ln2", "mlp", "out_epilogue", "rows_wait",
-          "gather_issue", "gather_landed"]
+          "mlp_wait", "mlp_tmem_ld"]
 
 
 def former_module_phases(cfg, blob, layer, kind, mode, v, XL=None):

@@ -147,15 +147,23 @@ inline size_t walk_image(const kasf_config* c, GlobalImg* G, LayerImg* L /* [n_l
 // ------------------------------------------------------------------ packed blob (bytes)
 // [ global block ][ layer 0 ][ layer 1 ] ...
 //   layer   = 6 x module + fusion block
-//   module  = vector block (fp32) + 12 weight chunks (bf16 [128 x 128] operand tiles, 32 KB each)
+//   module  = vector block (fp32) + 12 weight chunks ([128 x 128] 16-bit operand tiles, 32 KB each: bf16, except
+//             the fc2 chunks 8..11, which are fp16 like the hidden activation they multiply)
+// 1 (default): the MLP hidden activation and the fc2 weights are fp16 and the GELU epilogue runs in packed half
+// precision; 0: bf16 hidden tile, fp32 epilogue (kept for A/B measurements)
+#ifndef KASF_HALF_GELU
+#define KASF_HALF_GELU 1
+#endif
 constexpr size_t CHUNK_BYTES = 32768;
 constexpr int MOD_CHUNKS = 12;
 // vector block, offsets in floats
 constexpr int V_LS1 = 0, V_LS2 = 128, V_N1W = 256, V_N1B = 384, V_NLW = 512, V_NLB = 640, V_N2W = 768,
               V_N2B = 896, V_BMIX = 1024 /* proj bias | U bias */, V_BV = 1152, V_B1 = 1280, V_B2 = 1792,
-              V_BNS = 1920 /* [256] */, V_BNT = 2176 /* [256] */, V_FLOATS = 2560;
-constexpr size_t MOD_VEC_BYTES = V_FLOATS * 4;                                  // 10240
-constexpr size_t MOD_BYTES = MOD_VEC_BYTES + MOD_CHUNKS * CHUNK_BYTES;          // 403456
+              V_BNS = 1920 /* [256] */, V_BNT = 2176 /* [256] */,
+              V_B1H = 2560 /* fc1 bias as 512 fp16 values (256 floats) for the packed-half GELU epilogue */,
+              V_FLOATS = 2816;
+constexpr size_t MOD_VEC_BYTES = V_FLOATS * 4;                                  // 11264
+constexpr size_t MOD_BYTES = MOD_VEC_BYTES + MOD_CHUNKS * CHUNK_BYTES;          // 404480
 constexpr size_t FUSION_BYTES = 5120;                                            // W[3][384], b[3] fp32
 constexpr size_t LAYER_BYTES = 6 * MOD_BYTES + FUSION_BYTES;
 // chunk order inside a module (natural order; the kernel's producer walks its own sequence):

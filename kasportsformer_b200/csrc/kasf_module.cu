@@ -27,7 +27,7 @@
 // Shared memory map (bytes):   AUX    K|V bf16 / z fp32 / MLP hidden tiles                 65536
 //                              ATILE  bf16 A operand [128 x 128] (also Q, attention output)  32768
 //                              RING   3 x weight chunk [128 x 128] bf16                      98304
-//                              VEC    the module's fp32 vectors (LN, layer scale, biases)     10240
+//                              VEC    the module's fp32 vectors (LN, layer scale, biases)     11264
 //                              LN partials, adjacency bit masks, degrees, barriers
 // Tensor memory columns:       0..127 Q -> mixer output -> hidden chunk 0 | 128..255 K -> hidden chunk 1
 //                              256..383 V -> fc2 accumulator             | 384..511 residual rows X
@@ -58,14 +58,14 @@ constexpr uint32_t SM_A0 = SM_B0, SM_A1 = SM_B0;      // A operand tile (one buf
 #endif
 constexpr uint32_t SM_RING = 98304 + KASF_RING_SHIFT;
 constexpr uint32_t SM_VEC = SM_RING + RING * 32768;
-constexpr uint32_t SM_PART = SM_VEC + 10240;          // float2 [128][2]
+constexpr uint32_t SM_PART = SM_VEC + (uint32_t)MOD_VEC_BYTES;   // float2 [128][2]
 constexpr uint32_t SM_ADJ = SM_PART + 2048;           // u32 [128][4]
 constexpr uint32_t SM_ROWSUM = SM_ADJ + 2048;         // f32 [128]
 constexpr uint32_t SM_RSD = SM_ROWSUM + 512;          // f32 [128]  degree^-1/2 of the temporal adjacency rows
 constexpr uint32_t SM_BARS = SM_RSD + 512;
 constexpr uint32_t SM_TOTAL = SM_BARS + 256;
 static_assert(SM_TOTAL <= 232448, "shared memory budget");
-static_assert(MOD_VEC_BYTES == 10240, "vector block size");
+static_assert(MOD_VEC_BYTES == 11264, "vector block size");
 
 constexpr uint32_t TM_MIX = 0, TM_K = 128, TM_V = 256, TM_X = 384;   // mixer phase (Q lives at TM_MIX)
 constexpr uint32_t TM_H0 = 0, TM_H1 = 128, TM_OUT = 256;            // MLP phase
@@ -74,8 +74,10 @@ constexpr uint32_t TM_H0 = 0, TM_H1 = 128, TM_OUT = 256;            // MLP phase
 // operand tile is written), HSREADY (hidden tile c written, hidden accumulator drained).  MMA warp -> compute
 // warps: MMA (mixer projections done), HFULL (fc1 chunk in TMEM), HSFREE (fc2 has read the hidden tile),
 // OUT (fc2 complete).  ROWS: the cp.async row gather of a tile has landed (one arrival per compute thread).
+// MMAK / MMAV (self-attention): K / V are in tensor memory -- they are drained to shared memory while the next
+// projection runs (one barrier each: a waiter may lag at most one phase behind an mbarrier).
 enum { B_FULL0 = 0, B_EMPTY0 = RING, B_AREADY = 2 * RING, B_MMA, B_HFULL0, B_HFULL1, B_HSREADY0, B_HSREADY1,
-       B_HSFREE0, B_HSFREE1, B_OUT, B_ROWS, B_COUNT };
+       B_HSFREE0, B_HSFREE1, B_OUT, B_ROWS, B_MMAK, B_MMAV, B_COUNT };
 static_assert(B_COUNT * 8 + 8 <= 256, "barrier block");
 
 struct ModParams {
@@ -110,7 +112,9 @@ __device__ __forceinline__ float gelu2_arg(float v) {
 #ifdef KASF_EXACT_GELU
     return v;
 #else
-    const float v2 = v * v;
+    // v^2 is clamped where the fitted polynomial peaks (1.70 at v^2 = 48.6): beyond |v| = 7 the tanh is saturated
+    // anyway, and the unclamped quartic would turn negative past |v| = 10.7
+    const float v2 = fminf(v * v, 48.5f);
     return v * fmaf(v2, fmaf(v2, -0.0003828259195935171f, 0.03722352208203997f), 0.7972238404651819f);
 #endif
 }
@@ -122,6 +126,26 @@ __device__ __forceinline__ float gelu2_tanh(float w) {
     asm volatile("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(w));
     return t;
 #endif
+}
+
+// The same in packed half precision (default): the fc1 accumulator is rounded to fp16 (2^-11; the hidden tile
+// that feeds fc2 is fp16 as well, so nothing is lost against the former bf16 tile, 2^-9), and bias, polynomial,
+// tanh (MUFU.TANH.F16) and the final FMA run on two columns per instruction: 5.5 issue slots per element instead
+// of 9-11, which leaves the epilogue bound by the MUFU pipe alone (8 cycles per warp instruction).  |fc1 output|
+// saturates at 65504 and 2*GELU overflows beyond 32752 -- three orders of magnitude above anything LayerNorm-fed
+// projections produce.
+__device__ __forceinline__ __half2 u2h(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ uint32_t h2u(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ __half2 gelu2_arg_h2(__half2 v) {
+    const __half2 s = __hmin2(__hmul2(v, v), __float2half2_rn(48.5f));
+    const __half2 p = __hfma2(s, __hfma2(s, __float2half2_rn(-0.0003828259195935171f), __float2half2_rn(0.03722352208203997f)),
+                              __float2half2_rn(0.7972238404651819f));
+    return __hmul2(v, p);
+}
+__device__ __forceinline__ __half2 tanh_h2(__half2 w) {
+    uint32_t t;
+    asm volatile("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(h2u(w)));
+    return u2h(t);
 }
 
 // fp32 [128][128] tile with XOR-swizzled 16-byte chunks: conflict-free both for "warp per row" and
@@ -415,40 +439,78 @@ __device__ __forceinline__ void similarity_topk_impl(uint8_t* sm, int warp, int 
         const int g = item / mtiles, mt = item - g * mtiles;
         const int gr0 = g * T, m0 = gr0 + mt * 16;
         const int ra = min(m0 + g8, 127), rb = min(m0 + g8 + 8, 127);
-        float s[MAXNT][4];
+        // hi*hi and the two cross terms accumulate in separate registers (short sequences): two independent MMA
+        // dependency chains per key tile instead of one three times as long
+        constexpr bool SPLIT_ACC = MAXNT <= 8;
+        float s[MAXNT][4], sx[SPLIT_ACC ? MAXNT : 1][4];
 #pragma unroll
         for (int nt = 0; nt < MAXNT; ++nt)
 #pragma unroll
             for (int i = 0; i < 4; ++i) s[nt][i] = 0.f;
-#pragma unroll 2
-        for (int ks = 0; ks < 16; ++ks) {           // K = 128 in steps of 8
-            // A fragment: (row g8 | g8+8, k = 8 ks + t4 | + 4)
-            float av[4];
-            av[0] = *reinterpret_cast<const float*>(sm + SM_Z + f32_off(ra, 2 * ks) + t4 * 4);
-            av[1] = *reinterpret_cast<const float*>(sm + SM_Z + f32_off(rb, 2 * ks) + t4 * 4);
-            av[2] = *reinterpret_cast<const float*>(sm + SM_Z + f32_off(ra, 2 * ks + 1) + t4 * 4);
-            av[3] = *reinterpret_cast<const float*>(sm + SM_Z + f32_off(rb, 2 * ks + 1) + t4 * 4);
-            uint32_t ah[4], al[4];
+        if (SPLIT_ACC) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                ah[i] = __float_as_uint(av[i]) & 0xffffe000u;
-                al[i] = __float_as_uint(av[i] - __uint_as_float(ah[i]));
-            }
+            for (int nt = 0; nt < MAXNT; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) sx[nt][i] = 0.f;
+        }
+        // K = 128 in eight double steps of 16 columns.  The k index of an MMA is a free permutation as long as A and B
+        // agree: lane t4 of a quad takes the four consecutive columns 16 d + 4 t4 .. + 3 of its rows with ONE 128-bit
+        // load (first k-step: columns +0 / +1 in slots t4 / t4+4, second k-step: +2 / +3), and every address is a
+        // per-row base plus an immediate (scalar loads with per-load swizzle arithmetic made this phase
+        // instruction-bound: 3.9k instructions per work item).
+        const uint32_t zbase = SM_Z;   // offsets from sm: plain shared-memory loads the compiler may schedule freely
+        const uint32_t zrow_a = zbase + ra * 512 + ((t4 ^ (ra & 7)) << 4);
+        const uint32_t zrow_b = zbase + rb * 512 + ((t4 ^ (rb & 7)) << 4);
+        uint32_t zrow_j[MAXNT];
+#pragma unroll
+        for (int nt = 0; nt < MAXNT; ++nt) {
+            const int rj = min(gr0 + 8 * nt + g8, 127);
+            zrow_j[nt] = zbase + rj * 512 + ((t4 ^ (rj & 7)) << 4);
+        }
+        auto split = [](float v, uint32_t& hi, uint32_t& lo) {
+            hi = __float_as_uint(v) & 0xffffe000u;
+            lo = __float_as_uint(v - __uint_as_float(hi));
+        };
+#ifdef KASF_DBG_SKIP_SIM
+#pragma unroll 1
+        for (int d = 0; d < 0; ++d) {
+#else
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+#endif
+            // chunk 4 d + t4: 128-byte segment d >> 1, swizzled slot (t4 ^ x) [^ 4 for odd d]
+            const int off = (d >> 1) * 128;
+            const float4 fa = *reinterpret_cast<const float4*>(sm + ((zrow_a + off) ^ ((d & 1) << 6)));
+            const float4 fb = *reinterpret_cast<const float4*>(sm + ((zrow_b + off) ^ ((d & 1) << 6)));
+            uint32_t ah[2][4], al[2][4];
+            split(fa.x, ah[0][0], al[0][0]), split(fb.x, ah[0][1], al[0][1]), split(fa.y, ah[0][2], al[0][2]), split(fb.y, ah[0][3], al[0][3]);
+            split(fa.z, ah[1][0], al[1][0]), split(fb.z, ah[1][1], al[1][1]), split(fa.w, ah[1][2], al[1][2]), split(fb.w, ah[1][3], al[1][3]);
 #pragma unroll
             for (int nt = 0; nt < MAXNT; ++nt) {
                 if (nt < nkt) {
-                    // B fragment: (k = 8 ks + t4 | + 4, n = key 8 nt + g8)
-                    const int rj = min(gr0 + 8 * nt + g8, 127);
-                    const float b0 = *reinterpret_cast<const float*>(sm + SM_Z + f32_off(rj, 2 * ks) + t4 * 4);
-                    const float b1 = *reinterpret_cast<const float*>(sm + SM_Z + f32_off(rj, 2 * ks + 1) + t4 * 4);
-                    const uint32_t bh0 = __float_as_uint(b0) & 0xffffe000u, bh1 = __float_as_uint(b1) & 0xffffe000u;
-                    const uint32_t bl0 = __float_as_uint(b0 - __uint_as_float(bh0));
-                    const uint32_t bl1 = __float_as_uint(b1 - __uint_as_float(bh1));
-                    mma_tf32_1688(s[nt], al, bh0, bh1);
-                    mma_tf32_1688(s[nt], ah, bl0, bl1);
-                    mma_tf32_1688(s[nt], ah, bh0, bh1);
+                    const float4 fj = *reinterpret_cast<const float4*>(sm + ((zrow_j[nt] + off) ^ ((d & 1) << 6)));
+                    uint32_t bh[4], bl[4];
+                    split(fj.x, bh[0], bl[0]), split(fj.y, bh[1], bl[1]), split(fj.z, bh[2], bl[2]), split(fj.w, bh[3], bl[3]);
+#pragma unroll
+                    for (int k2 = 0; k2 < 2; ++k2) {
+                        if (SPLIT_ACC) {
+                            mma_tf32_1688(s[nt], ah[k2], bh[2 * k2], bh[2 * k2 + 1]);
+                            mma_tf32_1688(sx[nt], al[k2], bh[2 * k2], bh[2 * k2 + 1]);
+                            mma_tf32_1688(sx[nt], ah[k2], bl[2 * k2], bl[2 * k2 + 1]);
+                        } else {
+                            mma_tf32_1688(s[nt], al[k2], bh[2 * k2], bh[2 * k2 + 1]);
+                            mma_tf32_1688(s[nt], ah[k2], bl[2 * k2], bl[2 * k2 + 1]);
+                            mma_tf32_1688(s[nt], ah[k2], bh[2 * k2], bh[2 * k2 + 1]);
+                        }
+                    }
                 }
             }
+        }
+        if (SPLIT_ACC) {
+#pragma unroll
+            for (int nt = 0; nt < MAXNT; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) s[nt][i] += sx[nt][i];
         }
         // ---- rows g8 (values s[nt][0..1]) and g8+8 (s[nt][2..3]); a row is spread over the 4 lanes of a quad
 #pragma unroll
@@ -460,8 +522,12 @@ __device__ __forceinline__ void similarity_topk_impl(uint8_t* sm, int warp, int 
                 for (int i = 0; i < 2; ++i)
                     v[nt][i] = (nt < nkt && nt * 8 + t4 * 2 + i < T) ? s[nt][hrow * 2 + i] : -INFINITY;
             float thr = 0.f;
+#ifdef KASF_DBG_SKIP_TOPK
+            for (int it = 0; it < 0; ++it) {
+#else
 #pragma unroll 1
             for (int it = 0; it < 4; ++it) {
+#endif
                 float lm = -INFINITY;
 #pragma unroll
                 for (int nt = 0; nt < MAXNT; ++nt) lm = fmaxf(lm, fmaxf(v[nt][0], v[nt][1]));
@@ -614,7 +680,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
     constexpr int NCH = KIND == KASF_KIND_GRAPH ? 10 : (POST ? 9 : 12);
     constexpr int ORD_POST[12] = {3, 4, 5, 6, 8, 7, 9, 10, 11, 0, 0, 0};   // attention / bone tail: projection + MLP
     //                         mixer chunks                         MLP: W1_0 W1_1 W1_2 W2_0 W1_3 W2_1 W2_2 W2_3
-    constexpr int ORD_ATT[12] = {0, 1, 2, 3, 4, 5, 6, 8, 7, 9, 10, 11};
+    constexpr int ORD_ATT[12] = {1, 2, 0, 3, 4, 5, 6, 8, 7, 9, 10, 11};   // K, V, Q: K|V drain while Q runs
     constexpr int ORD_BONE[12] = {1, 2, 0, 3, 4, 5, 6, 8, 7, 9, 10, 11};
     constexpr int ORD_GCN[12] = {0, 1, 4, 5, 6, 8, 7, 9, 10, 11, 0, 0};
     const float* first_src = (KIND == KASF_KIND_BONE && !POST) ? p.xl : p.in;
@@ -644,10 +710,10 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
             const uint32_t a0_addr = smem_u32(sm + SM_A0), a1_addr = smem_u32(sm + SM_A1), ring_addr = smem_u32(sm + SM_RING),
                            hs_addr = smem_u32(sm + SM_HS);
             uint32_t cslot = 0, cph = 0, ph_a = 0, ph_hs0 = 0, ph_hs1 = 0;
-            auto chunk = [&](uint32_t tcol, uint32_t a_smem, bool acc) {
+            auto chunk = [&](uint32_t tcol, uint32_t a_smem, bool acc, bool fp16_operands = false) {
                 mbar_wait(&bars[B_FULL0 + cslot], cph);
                 tc_fence_after();
-                umma_tile_k128(tmem + tcol, a_smem, ring_addr + cslot * CHUNK_BYTES, 128, acc);
+                umma_tile_k128(tmem + tcol, a_smem, ring_addr + cslot * CHUNK_BYTES, 128, acc, fp16_operands);
                 tc_commit(&bars[B_EMPTY0 + cslot]);
                 if (++cslot == RING) cslot = 0, cph ^= 1;
             };
@@ -661,9 +727,11 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                     // Q, K, V were projected by the pre kernel
                 } else if (KIND == KASF_KIND_ATTENTION) {
                     wait_a();                                  // LN1(x)
-                    chunk(TM_MIX, a1_addr, false);             // Q
                     chunk(TM_K, a1_addr, false);
+                    tc_commit(&bars[B_MMAK]);
                     chunk(TM_V, a1_addr, false);
+                    tc_commit(&bars[B_MMAV]);
+                    chunk(TM_MIX, a1_addr, false);             // Q last: it is drained into the A tile itself
                     tc_commit(&bars[B_MMA]);
                 } else if (KIND == KASF_KIND_BONE) {
                     wait_a();                                  // LN_limb(XL)
@@ -697,7 +765,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                         chunk(buf ? TM_H1 : TM_H0, a0_addr, false);
                         tc_commit(&bars[buf ? B_HFULL1 : B_HFULL0]);
                     }
-                    chunk(TM_OUT, hs_addr + buf * TILE_BYTES, c > 0);
+                    chunk(TM_OUT, hs_addr + buf * TILE_BYTES, c > 0, KASF_HALF_GELU != 0);   // fc2: fp16 x fp16
                     if (c < 2) tc_commit(&bars[buf ? B_HSFREE1 : B_HSFREE0]);
                     if (c == 3) tc_commit(&bars[B_OUT]);
                 }
@@ -713,7 +781,8 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
         e.warp = warp;
         e.tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         WaitBar mma{&bars[B_MMA], 0}, hfull0{&bars[B_HFULL0], 0}, hfull1{&bars[B_HFULL1], 0},
-            hsfree0{&bars[B_HSFREE0], 0}, hsfree1{&bars[B_HSFREE1], 0}, outb{&bars[B_OUT], 0}, rows{&bars[B_ROWS], 0};
+            hsfree0{&bars[B_HSFREE0], 0}, hsfree1{&bars[B_HSFREE1], 0}, outb{&bars[B_OUT], 0}, rows{&bars[B_ROWS], 0},
+            mmak{&bars[B_MMAK], 0}, mmav{&bars[B_MMAV], 0};
 
         long long pt0 = p.prof ? clock64() : 0;
 #define PMARK(k)                                                      \
@@ -782,13 +851,10 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 tc_fence_after();
                 PMARK(5);
             } else if (KIND != KASF_KIND_GRAPH) {
-                mma.wait();                                // Q (and K,V) in tensor memory
-                tc_fence_after();
-                PMARK(2);
-                // ---- Q,K,V: TMEM -> bf16 smem.  Q goes to the (now free) A tile in operand layout, where the
-                //      attention output later replaces it block by block; K|V go to AUX (row pitch 512 B).
-#pragma unroll
-                for (int qkv = 0; qkv < 3; ++qkv)
+                // ---- Q,K,V: TMEM -> bf16 smem.  K|V go to AUX (row pitch 512 B) as soon as they are complete -- while
+                //      the next projection still runs on the tensor cores; Q goes last, into the (then free) A tile
+                //      in operand layout, where the attention output later replaces it block by block.
+                auto drain = [&](int qkv) {
 #pragma unroll
                     for (int b = 0; b < 2; ++b) {
                         uint32_t acc[32];
@@ -809,6 +875,24 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                             }
                         }
                     }
+                };
+                if (KIND == KASF_KIND_ATTENTION) {
+                    // K complete => every warp has arrived on AREADY, i.e. has read its staged rows: AUX is free
+                    mmak.wait();
+                    tc_fence_after();
+                    drain(1);
+                    mmav.wait();
+                    tc_fence_after();
+                    drain(2);
+                } else {
+                    csync();                               // every residual row has left the staging buffer (= AUX)
+                    drain(1);                              // K,V were complete before LN1(x) was written
+                    drain(2);
+                }
+                mma.wait();                                // Q in tensor memory
+                tc_fence_after();
+                PMARK(2);
+                drain(0);
                 csync();                                   // every warp reads the K|V rows of the others
                 PMARK(3);
                 attention_core<MODE, TC>(sm, warp, lane, gsize, nrows);
@@ -950,22 +1034,54 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
             warp_arrive(&bars[B_AREADY], lane);
             PMARK(10);
 
-            // ---- MLP epilogues: hidden chunk c (fc1 accumulator in TMEM) -> 2*GELU -> bf16 A operand tile AUX[c & 1]
+            // ---- MLP epilogues: hidden chunk c (fc1 accumulator in TMEM) -> 2*GELU -> 16-bit A operand tile AUX[c & 1]
+            //      (requesting the next 32 accumulator columns while the current ones are computed was measured
+            //       slower: tcgen05.ld next to running MMAs has ~250 cycles of latency either way, and the shorter
+            //       software pipelines lose more than the overlap wins)
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 const int buf = c & 1;
                 if (buf) hfull1.wait(); else hfull0.wait();
                 tc_fence_after();
                 if (c >= 2) { if (buf) hsfree1.wait(); else hsfree0.wait(); }
+                PMARK(14);
                 uint32_t acc[2][32];
                 tmem_ld32(e.tbase + (buf ? TM_H1 : TM_H0) + e.half * 64, acc[0]);
                 tmem_ld32(e.tbase + (buf ? TM_H1 : TM_H0) + e.half * 64 + 32, acc[1]);
                 tmem_ld_wait();
+                PMARK(15);
                 // two-stage software pipeline over groups of 8 columns: the tanh arguments of group g+1 are computed
                 // while the MUFU results of group g are in flight (the compiler's own schedule consumed each result
                 // a few instructions after issuing it: 1960 vs 1440 cycles per chunk, scripts/micro/gelu_epi.cu)
-                const float* b1 = vec + V_B1 + c * 128 + e.half * 64;
                 uint8_t* hs = sm + SM_HS + buf * TILE_BYTES;
+#if KASF_HALF_GELU
+                const uint4* b1h = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(vec + V_B1H) + c * 128 + e.half * 64);
+                __half2 v[2][4], w[2][4];
+                auto stage1 = [&](int g, int s2) {
+                    const uint4 bh = b1h[g];
+                    const uint32_t* a8 = &acc[g >> 2][(g & 3) * 8];
+                    v[s2][0] = __hadd2(u2h(pack_f16(__uint_as_float(a8[0]), __uint_as_float(a8[1]))), u2h(bh.x));
+                    v[s2][1] = __hadd2(u2h(pack_f16(__uint_as_float(a8[2]), __uint_as_float(a8[3]))), u2h(bh.y));
+                    v[s2][2] = __hadd2(u2h(pack_f16(__uint_as_float(a8[4]), __uint_as_float(a8[5]))), u2h(bh.z));
+                    v[s2][3] = __hadd2(u2h(pack_f16(__uint_as_float(a8[6]), __uint_as_float(a8[7]))), u2h(bh.w));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) w[s2][i] = gelu2_arg_h2(v[s2][i]);
+                };
+                stage1(0, 0);
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const int s2 = g & 1;
+                    __half2 t[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) t[i] = tanh_h2(w[s2][i]);
+                    if (g + 1 < 8) stage1(g + 1, s2 ^ 1);
+                    uint4 pk;
+                    pk.x = h2u(__hfma2(v[s2][0], t[0], v[s2][0])), pk.y = h2u(__hfma2(v[s2][1], t[1], v[s2][1]));
+                    pk.z = h2u(__hfma2(v[s2][2], t[2], v[s2][2])), pk.w = h2u(__hfma2(v[s2][3], t[3], v[s2][3]));
+                    *reinterpret_cast<uint4*>(hs + tile_off_bf16(e.row, e.half * 64 + g * 8)) = pk;
+                }
+#else
+                const float* b1 = vec + V_B1 + c * 128 + e.half * 64;
                 float v[2][8], w[2][8];
                 auto stage1 = [&](int g, int s2) {
                     const float4 ba = *reinterpret_cast<const float4*>(b1 + g * 8);
@@ -993,15 +1109,19 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                     pk.w = pack_bf16(fmaf(v[s2][6], t[6], v[s2][6]), fmaf(v[s2][7], t[7], v[s2][7]));
                     *reinterpret_cast<uint4*>(hs + tile_off_bf16(e.row, e.half * 64 + g * 8)) = pk;
                 }
+#endif
                 warp_arrive(&bars[buf ? B_HSREADY1 : B_HSREADY0], lane);
+                PMARK(11);
             }
             outb.wait();
             tc_fence_after();
-            PMARK(11);
+            PMARK(14);
             // ---- B1|B2 are free: request the next tile's rows; they land while the output epilogue runs
             if (tile + (int)gridDim.x < p.ntiles)
                 gather_rows<MODE>(p, sm, tile + (int)gridDim.x, first_src, &bars[B_ROWS], warp, lane);
             // ---- out = x1 + ls2 * (acc + b2): 256-bit stores of this thread's 64 columns, straight from registers
+            //      (staging the rows in shared memory for coalesced 128-bit stores was measured slower: 4.4k vs 3.4k
+            //       cycles per tile, the extra CTA barriers and the second pass over the data cost more than the LSU saves)
             {
                 float* orow = p.out + (tok >= 0 ? tok : 0) * D + e.half * 64;
 #pragma unroll

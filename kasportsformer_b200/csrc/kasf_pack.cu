@@ -45,8 +45,14 @@ __global__ void pack_chunks_kernel(const float* __restrict__ img, uint8_t* __res
             v0 = src[(size_t)n * ld + k];
             v1 = src[(size_t)n * ld + k + 1];
         }
-        if (c >= 8) v0 *= 0.5f, v1 *= 0.5f;   // the MLP epilogue produces 2*GELU (exact power-of-two rescaling)
-        *reinterpret_cast<uint32_t*>(dst + tile_off_bf16(n, k)) = pack_bf16(v0, v1);
+        if (c >= 8 && !KASF_HALF_GELU) {
+            *reinterpret_cast<uint32_t*>(dst + tile_off_bf16(n, k)) = pack_bf16(0.5f * v0, 0.5f * v1);
+        } else if (c >= 8) {
+            // the MLP epilogue produces 2*GELU (exact power-of-two rescaling) as fp16: fc2 is an f16 x f16 MMA
+            *reinterpret_cast<uint32_t*>(dst + tile_off_bf16(n, k)) = pack_f16(0.5f * v0, 0.5f * v1);
+        } else {
+            *reinterpret_cast<uint32_t*>(dst + tile_off_bf16(n, k)) = pack_bf16(v0, v1);
+        }
     }
 }
 
@@ -80,7 +86,10 @@ __global__ void pack_vectors_kernel(const float* __restrict__ img, uint8_t* __re
             v[V_BMIX + i] = img[m.projb + i];
         }
     }
-    for (int i = threadIdx.x; i < HID; i += blockDim.x) v[V_B1 + i] = img[m.fc1b + i];
+    for (int i = threadIdx.x; i < HID; i += blockDim.x) {
+        v[V_B1 + i] = img[m.fc1b + i];
+        reinterpret_cast<__half*>(v + V_B1H)[i] = __float2half_rn(img[m.fc1b + i]);
+    }
     if (pm.kind == 1)
         for (int i = threadIdx.x; i < pm.nodes; i += blockDim.x) {
             // eval BatchNorm: y*s + t,  s = w / sqrt(var + eps),  t = b - mean * s

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace kasf {
@@ -110,7 +111,7 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
                      smem_u32(bar))
                  : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 inputs, fp32 accumulate
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, 16-bit float inputs (bf16 or fp16, see the instruction descriptor), fp32 accumulate
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                           uint32_t accumulate) {
     asm volatile(
@@ -142,6 +143,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
+}
+
+// wait for the outstanding tcgen05.ld of this thread; the destination registers are in/out operands so that the
+// compiler cannot schedule a use of them above the wait (needed when independent work sits between ld and wait)
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
 }
 
 // registers -> TMEM, 32 consecutive columns of this thread's lane
@@ -184,6 +197,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
     return d;
 }
+// Instruction descriptor: kind::f16, A=B=fp16 (format code 0), D=fp32, both K-major, shape M x N (K = 16).
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
+    return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 // Instruction descriptor: kind::f16, A=B=bf16, D=fp32, both K-major, shape M x N (K = 16).
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
     return (1u << 4)            // D format: f32
@@ -206,11 +223,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
+// two fp32 -> packed fp16x2 (round to nearest, saturating to the largest finite half instead of infinity)
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 
 // Issue the 8 K-steps (K = 128) of D[128 x N] (+)= A_tile * B_tile^T.  One thread.
 __device__ __forceinline__ void umma_tile_k128(uint32_t tmem_d, uint32_t a_smem, uint32_t b_smem, uint32_t N,
-                                               bool accumulate_first) {
-    const uint32_t idesc = umma_idesc_bf16(128, N);
+                                               bool accumulate_first, bool fp16_operands = false) {
+    const uint32_t idesc = fp16_operands ? umma_idesc_f16(128, N) : umma_idesc_bf16(128, N);
     // the start-address field (16-byte units) is the only part of the descriptor that moves with the K-step
     const uint64_t da = umma_desc_sw128(a_smem), db = umma_desc_sw128(b_smem);
 #pragma unroll

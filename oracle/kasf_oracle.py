@@ -207,6 +207,10 @@ def gcn_mixer(state: State, pre: str, z: Tensor, mode: str, neighbour_num: int,
 def mlp(state: State, pre: str, z: Tensor) -> Tensor:
     """reference model/modules/mlp.py:24-30."""
     h = gelu_erf(linear(z, state[pre + "fc1.weight"], state[pre + "fc1.bias"]))
+    if EMULATE_BF16:
+        # the kernels keep the hidden activation and the fc2 weights in fp16 (fc2 is an f16 x f16 -> fp32 MMA)
+        w2 = state[pre + "fc2.weight"]
+        return F.linear(h.to(torch.float16).to(h.dtype), w2.to(torch.float16).to(w2.dtype), state[pre + "fc2.bias"])
     return linear(h, state[pre + "fc2.weight"], state[pre + "fc2.bias"])
 
 
