@@ -132,6 +132,20 @@ int kasf_former_module_ws(const kasf_config* cfg, const void* packed_dev, int la
                           int mode, const float* in_dev, const float* XL_dev, float* out_dev, int B,
                           void* scratch_dev, size_t scratch_bytes, void* stream);
 
+/* Bone modules, fast path: the limb stream is the same for every layer and the limb LayerNorm's affine is folded
+ * into the packed K|V weights, so the K|V operand of all bone modules is the normalised limb row.  kasf_limb_tiles
+ * normalises XL once (fp32 two-pass statistics, model/modules/bone_crossattention.py:47-51) and writes it as bf16
+ * [128 x 128] operand tiles in the tile order of `mode`; a bone module of the same mode given `limb_tiles_dev`
+ * (128-byte aligned, kasf_limb_tiles_bytes bytes) fetches its K|V operand with one bulk copy per tile and never
+ * reads XL_dev.  kasf_limb_tiles_bytes is 0 for temporal tiles with n_frames > 128 (the split path reads XL_dev);
+ * pass NULL then.  kasf_forward uses this path internally. */
+size_t kasf_limb_tiles_bytes(const kasf_config* cfg, int B, int mode);
+int kasf_limb_tiles(const kasf_config* cfg, const float* XL_dev, void* limb_tiles_dev, int B, int mode,
+                    void* stream);
+int kasf_former_module_lt(const kasf_config* cfg, const void* packed_dev, int layer, int kind, int mode,
+                          const float* in_dev, const float* XL_dev, const void* limb_tiles_dev,
+                          float* out_dev, int B, void* scratch_dev, size_t scratch_bytes, void* stream);
+
 /* Profiling hook: same launch, additionally accumulating (atomicAdd by thread 0 of every CTA) the SM cycles
  * spent in each phase of the kernel into phase_cycles_dev[16] (caller zeroes it): 0 limb K/V, 1 load+LN1,
  * 2 QKV MMA wait, 3 Q/K/V drain, 4 attention core, 5 projection MMA wait, 6 similarity/top-k, 7 aggregation,

@@ -62,6 +62,11 @@ _SIGNATURES = {
     "kasf_kinematic_features": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                           C.c_void_p]),
+    "kasf_limb_tiles_bytes": (C.c_size_t, [C.POINTER(KasfConfig), C.c_int, C.c_int]),
+    "kasf_limb_tiles": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "kasf_former_module_lt": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t,
+                                        C.c_void_p]),
     "kasf_former_module": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "kasf_former_module_profiled": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_int, C.c_int, C.c_int,
@@ -264,16 +269,38 @@ def kinematic_features(cfg, blob, x, want_raw=True):
     return bone, limb, X, XB, XL
 
 
-def former_module(cfg, blob, layer, kind, mode, v, XL=None, out=None):
+def limb_tiles(cfg, XL, mode):
+    """Normalised limb rows as bf16 operand tiles in the tile order of `mode` (None when the mode has no tile path)."""
+    _require_device(XL.device)
+    B = XL.shape[0]
+    n = lib().kasf_limb_tiles_bytes(C.byref(c_config(cfg)), B, MODE[mode])
+    if n == 0:
+        return None
+    tiles = torch.empty(n, dtype=torch.uint8, device=XL.device)
+    with torch.cuda.device(XL.device):
+        _check(lib().kasf_limb_tiles(C.byref(c_config(cfg)), _ptr(XL), _ptr(tiles), B, MODE[mode], _stream()),
+               "kasf_limb_tiles")
+    return tiles
+
+
+def former_module(cfg, blob, layer, kind, mode, v, XL=None, out=None, use_limb_tiles=False):
+    """One FormerModule.  use_limb_tiles: bone modules take their K|V operand from pre-normalised limb tiles (the
+    path kasf_forward uses) instead of normalising XL inside the kernel."""
     _require_device(v.device)
     B = v.shape[0]
     out = torch.empty_like(v) if out is None else out
     with torch.cuda.device(v.device):
         nscr = lib().kasf_module_scratch_bytes(C.byref(c_config(cfg)), B) if mode == "temporal" else 0
         scr = torch.empty(max(nscr, 256), dtype=torch.uint8, device=v.device)
-        _check(lib().kasf_former_module_ws(C.byref(c_config(cfg)), _ptr(blob), layer, KIND[kind], MODE[mode],
-                                           _ptr(v), _ptr(XL), _ptr(out), B, _ptr(scr), nscr, _stream()),
-               "kasf_former_module_ws")
+        if use_limb_tiles and kind == "bone":
+            lt = limb_tiles(cfg, XL, mode)
+            _check(lib().kasf_former_module_lt(C.byref(c_config(cfg)), _ptr(blob), layer, KIND[kind], MODE[mode],
+                                               _ptr(v), _ptr(XL), _ptr(lt), _ptr(out), B, _ptr(scr), nscr, _stream()),
+                   "kasf_former_module_lt")
+        else:
+            _check(lib().kasf_former_module_ws(C.byref(c_config(cfg)), _ptr(blob), layer, KIND[kind], MODE[mode],
+                                               _ptr(v), _ptr(XL), _ptr(out), B, _ptr(scr), nscr, _stream()),
+                   "kasf_former_module_ws")
     return out
 
 

@@ -101,7 +101,8 @@ size_t kasf_workspace_bytes(const kasf_config* cfg, int B) {
     if (config_ok(cfg) || B <= 0) return 0;
     const int chunk = clip_chunk(cfg, B);
     const long long tokens = (long long)chunk * cfg->n_frames * J;
-    return 6 * (((size_t)tokens * D * 4 + 1023) / 1024 * 1024) + module_scratch_bytes(chunk, cfg->n_frames);
+    return 6 * (((size_t)tokens * D * 4 + 1023) / 1024 * 1024) + module_scratch_bytes(chunk, cfg->n_frames) +
+           limb_tiles_bytes(chunk, cfg->n_frames, KASF_MODE_SPATIAL) + limb_tiles_bytes(chunk, cfg->n_frames, KASF_MODE_TEMPORAL);
 }
 
 size_t kasf_module_scratch_bytes(const kasf_config* cfg, int B) {
@@ -122,7 +123,8 @@ int kasf_forward_launches(const kasf_config* cfg, int B) {
     const int passes = (B + chunk - 1) / chunk;
     // T > 128: a temporal module is 3 kernels (attention, bone) or 2 (graph) instead of 1
     const int per_layer = cfg->n_frames > 128 ? 7 + 2 + 1 + 2 : 7;
-    return passes * (1 + cfg->n_layers * per_layer + 1);
+    const int limb = cfg->n_frames > 128 ? 1 : 2;   // limb_tiles_kernel launches
+    return passes * (1 + limb + cfg->n_layers * per_layer + 1);
 }
 
 int kasf_kinematic_features(const kasf_config* cfg, const void* packed_dev, const float* x_dev, float* bone_dev,
@@ -144,6 +146,30 @@ int kasf_former_module_ws(const kasf_config* cfg, const void* packed_dev, int la
     if ((rc = device_ok())) return rc;
     return launch_former_module((const uint8_t*)packed_dev, layer, kind, mode, in_dev, XL_dev, out_dev, B,
                                 cfg->n_frames, (cudaStream_t)stream, nullptr, scratch_dev, scratch_bytes);
+}
+
+size_t kasf_limb_tiles_bytes(const kasf_config* cfg, int B, int mode) {
+    if (config_ok(cfg) || B <= 0 || mode < 0 || mode > 1) return 0;
+    return limb_tiles_bytes(B, cfg->n_frames, mode);
+}
+
+int kasf_limb_tiles(const kasf_config* cfg, const float* XL_dev, void* limb_tiles_dev, int B, int mode, void* stream) {
+    int rc = config_ok(cfg);
+    if (rc) return rc;
+    if (!XL_dev || !limb_tiles_dev || B < 0 || mode < 0 || mode > 1) return KASF_EINVAL;
+    if ((rc = device_ok())) return rc;
+    return launch_limb_tiles(XL_dev, limb_tiles_dev, B, cfg->n_frames, mode, (cudaStream_t)stream);
+}
+
+int kasf_former_module_lt(const kasf_config* cfg, const void* packed_dev, int layer, int kind, int mode,
+                          const float* in_dev, const float* XL_dev, const void* limb_tiles_dev, float* out_dev, int B,
+                          void* scratch_dev, size_t scratch_bytes, void* stream) {
+    int rc = config_ok(cfg);
+    if (rc) return rc;
+    if (!packed_dev || !in_dev || !out_dev || B < 0 || layer < 0 || layer >= cfg->n_layers) return KASF_EINVAL;
+    if ((rc = device_ok())) return rc;
+    return launch_former_module((const uint8_t*)packed_dev, layer, kind, mode, in_dev, XL_dev, out_dev, B,
+                                cfg->n_frames, (cudaStream_t)stream, nullptr, scratch_dev, scratch_bytes, limb_tiles_dev);
 }
 
 int kasf_former_module(const kasf_config* cfg, const void* packed_dev, int layer, int kind, int mode,
@@ -206,8 +232,14 @@ static int forward_impl(const kasf_config* cfg, const void* packed_dev, const fl
         const size_t stream_bytes = ((size_t)chunk * T * J * D * 4 + 1023) / 1024 * 1024;
         void* scr = static_cast<uint8_t*>(ws_dev) + 6 * stream_bytes;     // temporal modules, T > 128 only
         const size_t scr_bytes = module_scratch_bytes(chunk, T);
+        // normalised limb rows as bf16 operand tiles (spatial / temporal tile order), shared by all layers
+        uint8_t* lt_s = static_cast<uint8_t*>(scr) + scr_bytes;
+        uint8_t* lt_t = lt_s + limb_tiles_bytes(chunk, T, KASF_MODE_SPATIAL);
+        if (limb_tiles_bytes(chunk, T, KASF_MODE_TEMPORAL) == 0) lt_t = nullptr;
         const float* x = x_dev + (size_t)b0 * T * J * 3;
         if ((rc = launch_features(blob, x, nullptr, nullptr, s.X, s.XB, s.XL, (long long)nb * T, st))) return rc;
+        if ((rc = launch_limb_tiles(s.XL, lt_s, nb, T, KASF_MODE_SPATIAL, st))) return rc;
+        if ((rc = launch_limb_tiles(s.XL, lt_t, nb, T, KASF_MODE_TEMPORAL, st))) return rc;
         KASF_MARK();
         for (int l = 0; l < cfg->n_layers; ++l) {
             // three branches, each spatial module then temporal module (KASportsFormer.py:268-275)
@@ -220,9 +252,9 @@ static int forward_impl(const kasf_config* cfg, const void* packed_dev, const fl
             KASF_MARK();
             if ((rc = launch_former_module(blob, l, KASF_KIND_GRAPH, KASF_MODE_TEMPORAL, s.G, nullptr, s.G, nb, T, st, nullptr, scr, scr_bytes))) return rc;
             KASF_MARK();
-            if ((rc = launch_former_module(blob, l, KASF_KIND_BONE, KASF_MODE_SPATIAL, bone_src, s.XL, s.Bn, nb, T, st))) return rc;
+            if ((rc = launch_former_module(blob, l, KASF_KIND_BONE, KASF_MODE_SPATIAL, bone_src, s.XL, s.Bn, nb, T, st, nullptr, nullptr, 0, lt_s))) return rc;
             KASF_MARK();
-            if ((rc = launch_former_module(blob, l, KASF_KIND_BONE, KASF_MODE_TEMPORAL, s.Bn, s.XL, s.Bn, nb, T, st, nullptr, scr, scr_bytes))) return rc;
+            if ((rc = launch_former_module(blob, l, KASF_KIND_BONE, KASF_MODE_TEMPORAL, s.Bn, s.XL, s.Bn, nb, T, st, nullptr, scr, scr_bytes, lt_t))) return rc;
             KASF_MARK();
             if ((rc = launch_fusion(blob, l, s.A, s.G, s.Bn, s.X, tokens, st))) return rc;
             KASF_MARK();

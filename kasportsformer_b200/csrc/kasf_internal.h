@@ -25,7 +25,11 @@ int launch_fusion(const uint8_t* blob, int layer, const float* a, const float* g
 // `scratch` (module_scratch_bytes(B, T) bytes, 256-byte aligned) is needed by temporal modules with T > 128 only
 int launch_former_module(const uint8_t* blob, int layer, int kind, int mode, const float* in, const float* XL,
                          float* out, int B, int T, cudaStream_t st, unsigned long long* prof = nullptr,
-                         void* scratch = nullptr, size_t scratch_bytes = 0);
+                         void* scratch = nullptr, size_t scratch_bytes = 0, const void* limb_tiles = nullptr);
+// Pre-normalised limb rows as bf16 operand tiles in the tile order of `mode` (0 bytes for temporal, T > 128): the
+// optional `limb_tiles` argument of a bone module of the same mode.
+size_t limb_tiles_bytes(int B, int T, int mode);
+int launch_limb_tiles(const float* XL, void* tiles, int B, int T, int mode, cudaStream_t st);
 size_t module_scratch_bytes(int B, int T);
 int launch_metrics(int T, const float* pred, const float* pred_flip, const float* gt, const float* res,
                    const float* factor, const int32_t* action, int n_actions, double* sums, double* per_frame,

@@ -31,6 +31,8 @@
 //                              LN partials, adjacency bit masks, degrees, barriers
 // Tensor memory columns:       0..127 Q -> mixer output -> hidden chunk 0 | 128..255 K -> hidden chunk 1
 //                              256..383 V -> fc2 accumulator             | 384..511 residual rows X
+#include <cstring>
+
 #include "kasf_internal.h"
 
 namespace kasf {
@@ -74,10 +76,13 @@ constexpr uint32_t TM_H0 = 0, TM_H1 = 128, TM_OUT = 256;            // MLP phase
 // operand tile is written), HSREADY (hidden tile c written, hidden accumulator drained).  MMA warp -> compute
 // warps: MMA (mixer projections done), HFULL (fc1 chunk in TMEM), HSFREE (fc2 has read the hidden tile),
 // OUT (fc2 complete).  ROWS: the cp.async row gather of a tile has landed (one arrival per compute thread).
+// Bone modules fed from pre-normalised limb tiles: LIMBFULL (the tile's bf16 limb rows have landed in the A tile by
+// bulk copy), A0FREE (tcgen05.commit: the last MMA reading the A tile has completed, the producer may overwrite it),
+// OUTDONE (every compute warp has drained the fc2 accumulator of the previous tile: V may be projected into it).
 // MMAK / MMAV (self-attention): K / V are in tensor memory -- they are drained to shared memory while the next
 // projection runs (one barrier each: a waiter may lag at most one phase behind an mbarrier).
 enum { B_FULL0 = 0, B_EMPTY0 = RING, B_AREADY = 2 * RING, B_MMA, B_HFULL0, B_HFULL1, B_HSREADY0, B_HSREADY1,
-       B_HSFREE0, B_HSFREE1, B_OUT, B_ROWS, B_MMAK, B_MMAV, B_COUNT };
+       B_HSFREE0, B_HSFREE1, B_OUT, B_ROWS, B_MMAK, B_MMAV, B_LIMBFULL, B_A0FREE, B_OUTDONE, B_COUNT };
 static_assert(B_COUNT * 8 + 8 <= 256, "barrier block");
 
 struct ModParams {
@@ -94,6 +99,9 @@ struct ModParams {
     __nv_bfloat16* sk;       // [B*17*T, 128] K
     __nv_bfloat16* sv;       // [B*17*T, 128] V
     float* srow;             // [B*17*T] GCN: row sums of A_hat
+    // bone modules: optional pre-normalised limb rows, one bf16 [128 x 128] operand-tile image per tile of this mode
+    // (limb_tiles_kernel); null: the kernel normalises the fp32 limb rows itself
+    const uint8_t* xlt;
 };
 // internal row mapping of the split path: a tile is 128 consecutive rows of the (sequence, frame) order
 #define KASF_MODE_LONG 2
@@ -661,7 +669,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
         if ((smem_u32(sm) & 1023u) != 0) __trap();
         for (int i = 0; i < B_COUNT; ++i) {
             const bool by_warps = i == B_AREADY || i == B_HSREADY0 || i == B_HSREADY1;
-            mbar_init(&bars[i], by_warps ? CW : (i == B_ROWS ? CW * 32 : 1));
+            mbar_init(&bars[i], (by_warps || i == B_OUTDONE) ? CW : (i == B_ROWS ? CW * 32 : 1));
         }
         fence_mbar_init();
     }
@@ -683,7 +691,8 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
     constexpr int ORD_ATT[12] = {1, 2, 0, 3, 4, 5, 6, 8, 7, 9, 10, 11};   // K, V, Q: K|V drain while Q runs
     constexpr int ORD_BONE[12] = {1, 2, 0, 3, 4, 5, 6, 8, 7, 9, 10, 11};
     constexpr int ORD_GCN[12] = {0, 1, 4, 5, 6, 8, 7, 9, 10, 11, 0, 0};
-    const float* first_src = (KIND == KASF_KIND_BONE && !POST) ? p.xl : p.in;
+    const bool limb_tiles = KIND == KASF_KIND_BONE && !POST && p.xlt != nullptr;
+    const float* first_src = (KIND == KASF_KIND_BONE && !POST && !limb_tiles) ? p.xl : p.in;
 
     if (warp >= CW) {
         // ===================== service warpgroup (hands its registers to the compute warpgroups) =====================
@@ -692,7 +701,18 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
             // ---- weight chunks: L2 -> ring slots (bulk copies, MMA-ready swizzled images)
             if (lane == 0) {
                 uint32_t slot = 0, ph = 0;
+                uint32_t ph_free = 0;
                 for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                    if (limb_tiles) {
+                        // the tile's normalised limb rows: one 32 KB bulk copy straight into the A operand tile, as soon
+                        // as the previous tile's last fc1 chunk has read it
+                        if (tile != (int)blockIdx.x) {
+                            mbar_wait_suspend(&bars[B_A0FREE], ph_free);
+                            ph_free ^= 1;
+                        }
+                        mbar_arrive_expect_tx(&bars[B_LIMBFULL], TILE_BYTES);
+                        bulk_g2s(sm + SM_A1, p.xlt + (size_t)tile * TILE_BYTES, TILE_BYTES, &bars[B_LIMBFULL]);
+                    }
 #pragma unroll 1
                     for (int i = 0; i < NCH; ++i) {
                         const int ci = KIND == KASF_KIND_GRAPH ? ORD_GCN[i]
@@ -709,7 +729,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
             // ---- the only thread that issues tcgen05.mma
             const uint32_t a0_addr = smem_u32(sm + SM_A0), a1_addr = smem_u32(sm + SM_A1), ring_addr = smem_u32(sm + SM_RING),
                            hs_addr = smem_u32(sm + SM_HS);
-            uint32_t cslot = 0, cph = 0, ph_a = 0, ph_hs0 = 0, ph_hs1 = 0;
+            uint32_t cslot = 0, cph = 0, ph_a = 0, ph_hs0 = 0, ph_hs1 = 0, ph_limb = 0;
             auto chunk = [&](uint32_t tcol, uint32_t a_smem, bool acc, bool fp16_operands = false) {
                 mbar_wait(&bars[B_FULL0 + cslot], cph);
                 tc_fence_after();
@@ -734,9 +754,21 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                     chunk(TM_MIX, a1_addr, false);             // Q last: it is drained into the A tile itself
                     tc_commit(&bars[B_MMA]);
                 } else if (KIND == KASF_KIND_BONE) {
-                    wait_a();                                  // LN_limb(XL)
-                    chunk(TM_K, a1_addr, false);
-                    chunk(TM_V, a1_addr, false);
+                    if (limb_tiles) {
+                        // K|V of this tile are projected while the compute warps still run the previous tile's output
+                        // epilogue; V lands in the fc2 accumulator's columns and waits for them to be drained
+                        mbar_wait(&bars[B_LIMBFULL], ph_limb);
+                        tc_fence_after();
+                        chunk(TM_K, a1_addr, false);
+                        mbar_wait(&bars[B_OUTDONE], ph_limb);
+                        ph_limb ^= 1;
+                        tc_fence_after();
+                        chunk(TM_V, a1_addr, false);
+                    } else {
+                        wait_a();                              // LN_limb(XL)
+                        chunk(TM_K, a1_addr, false);
+                        chunk(TM_V, a1_addr, false);
+                    }
                     tc_commit(&bars[B_MMA]);
                     wait_a();                                  // LN1(x)
                     chunk(TM_MIX, a1_addr, false);             // Q
@@ -764,6 +796,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                     if (c < 2) {                               // fc1 chunk c+2 first: the epilogue warps wait for it
                         chunk(buf ? TM_H1 : TM_H0, a0_addr, false);
                         tc_commit(&bars[buf ? B_HFULL1 : B_HFULL0]);
+                        if (c == 1 && limb_tiles) tc_commit(&bars[B_A0FREE]);   // last reader of the A tile
                     }
                     chunk(TM_OUT, hs_addr + buf * TILE_BYTES, c > 0, KASF_HALF_GELU != 0);   // fc2: fp16 x fp16
                     if (c < 2) tc_commit(&bars[buf ? B_HSFREE1 : B_HSFREE0]);
@@ -795,6 +828,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
     } while (0)
 
         gather_rows<MODE>(p, sm, blockIdx.x, first_src, &bars[B_ROWS], warp, lane);
+        if (limb_tiles && lane == 0) mbar_arrive(&bars[B_OUTDONE]);   // no previous tile: the accumulator columns are free
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
             const int nrows = tile_rows<MODE>(p, tile);
             const int gsize = MODE == KASF_MODE_SPATIAL ? J : p.T;
@@ -803,7 +837,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
             float xv[64];
             float mean, rstd;
 
-            if (KIND == KASF_KIND_BONE && !POST) {
+            if (KIND == KASF_KIND_BONE && !POST && !limb_tiles) {
                 // ---- K,V from the limb stream: LN_limb(XL) Wkv^T
                 rows.wait();
                 read_staged(sm, e, xv, row_ok);
@@ -1148,6 +1182,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                     }
                 }
             }
+            if (limb_tiles) warp_arrive(&bars[B_OUTDONE], lane);   // fc2 accumulator drained: V of the next tile may land
             // (no CTA barrier here: the next tile's first shared-memory writes touch buffers whose last readers
             //  were MMAs already observed complete by every thread, and its MMAs wait for AREADY)
             PMARK(12);
@@ -1608,9 +1643,76 @@ static int launch_long(ModParams p, int kind, void* scratch, size_t scratch_byte
                                        : launch_one<KASF_KIND_BONE, KASF_MODE_LONG, 0>(p, st);
 }
 
+// ---------------------------------------------------------------------------------------------- limb tiles
+// The limb stream XL is the same for all 26 layers, and the limb LayerNorm's affine is folded into the K|V weights
+// (kasf_pack.cu), so the operand of every bone module's K|V projection is the normalised limb row itself.  This
+// kernel normalises XL once per forward and writes it, rounded to bf16, as ready-made [128 x 128] operand-tile
+// images (128-byte swizzle) in the tile order of the spatial (MODE 0) or temporal (MODE 1) modules: a bone module
+// then fetches its tile's limb operand with one 32 KB bulk copy and never touches the fp32 limb rows.
+// Warp per row, lane = 4 columns, exact two-pass fp32 statistics (eps 1e-5, bone_crossattention.py:47-51).
+template <int MODE>
+__global__ void __launch_bounds__(256) limb_tiles_kernel(const ModParams p, uint8_t* __restrict__ tiles) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        uint8_t* dst = tiles + (size_t)tile * TILE_BYTES;
+        const int n = tile_rows<MODE>(p, tile);
+        for (int r = warp; r < 128; r += 8) {
+            uint2 pk = make_uint2(0u, 0u);
+            if (r < n) {
+                const long long tok = row_token<MODE>(p, tile, r);
+                const float4 v = *reinterpret_cast<const float4*>(p.xl + tok * D + lane * 4);
+                float s = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                const float mean = s * (1.0f / D);
+                const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+                float q = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+                const float rstd = 1.0f / sqrtf(q * (1.0f / D) + 1e-5f);
+                pk.x = pack_bf16(d0 * rstd, d1 * rstd);
+                pk.y = pack_bf16(d2 * rstd, d3 * rstd);
+            }
+            *reinterpret_cast<uint2*>(dst + tile_off_bf16(r, lane * 4)) = pk;
+        }
+    }
+}
+
+static void mode_tiling(ModParams& p, int mode) {
+    if (mode == KASF_MODE_SPATIAL) {
+        p.groups_per_tile = 7;
+        p.ntiles = (int)(((long long)p.B * p.T + 6) / 7);
+    } else {
+        p.groups_per_tile = 128 / p.T;
+        p.ntiles = (int)(((long long)p.B * J + p.groups_per_tile - 1) / p.groups_per_tile);
+    }
+}
+
+size_t limb_tiles_bytes(int B, int T, int mode) {
+    if (mode == KASF_MODE_TEMPORAL && T > 128) return 0;   // split path: the projection kernel reads the fp32 rows
+    ModParams p;
+    p.B = B, p.T = T;
+    mode_tiling(p, mode);
+    return (size_t)p.ntiles * TILE_BYTES;
+}
+
+int launch_limb_tiles(const float* XL, void* tiles, int B, int T, int mode, cudaStream_t st) {
+    if (B <= 0 || limb_tiles_bytes(B, T, mode) == 0) return KASF_OK;
+    if (!XL || !tiles || ((uintptr_t)tiles & 127) != 0 || ((uintptr_t)XL & 15) != 0) return KASF_EINVAL;
+    ModParams p;
+    memset(&p, 0, sizeof p);
+    p.xl = XL;
+    p.B = B, p.T = T;
+    mode_tiling(p, mode);
+    const int grid = p.ntiles < 148 * 8 ? p.ntiles : 148 * 8;
+    if (mode == KASF_MODE_SPATIAL) limb_tiles_kernel<KASF_MODE_SPATIAL><<<grid, 256, 0, st>>>(p, static_cast<uint8_t*>(tiles));
+    else limb_tiles_kernel<KASF_MODE_TEMPORAL><<<grid, 256, 0, st>>>(p, static_cast<uint8_t*>(tiles));
+    return cuda_status();
+}
+
 int launch_former_module(const uint8_t* blob, int layer, int kind, int mode, const float* in, const float* XL,
                          float* out, int B, int T, cudaStream_t st, unsigned long long* prof, void* scratch,
-                         size_t scratch_bytes) {
+                         size_t scratch_bytes, const void* limb_tiles) {
     if (B <= 0) return KASF_OK;
     if (kind < 0 || kind > 2 || mode < 0 || mode > 1) return KASF_EINVAL;
     if (kind == KASF_KIND_BONE && !XL) return KASF_EINVAL;
@@ -1627,6 +1729,8 @@ int launch_former_module(const uint8_t* blob, int layer, int kind, int mode, con
     p.prof = prof;
     p.sq = p.sk = p.sv = nullptr;
     p.srow = nullptr;
+    p.xlt = kind == KASF_KIND_BONE ? static_cast<const uint8_t*>(limb_tiles) : nullptr;
+    if (((uintptr_t)p.xlt & 127) != 0) return KASF_EINVAL;
     if (mode == KASF_MODE_TEMPORAL && T > 128) return launch_long(p, kind, scratch, scratch_bytes, st);
     int tc = 0;
     if (mode == KASF_MODE_SPATIAL) {

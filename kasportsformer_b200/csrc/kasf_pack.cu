@@ -38,6 +38,10 @@ __global__ void pack_chunks_kernel(const float* __restrict__ img, uint8_t* __res
         src = c == 0 ? img + pm.img.Uw : (c == 1 ? img + pm.img.Vw : nullptr);
     }
     uint8_t* dst = blob + pm.dst + MOD_VEC_BYTES + (size_t)c * CHUNK_BYTES;
+    // bone K|V projections: the limb LayerNorm's gamma is folded into the weight columns, so that the operand is the
+    // layer-independent normalised limb row (computed once per forward, see limb_tiles_kernel); beta goes to the
+    // output-projection bias (pack_vectors_kernel)
+    const float* kscale = (pm.kind == 2 && (c == 1 || c == 2)) ? img + pm.img.nlw : nullptr;
     for (int i = threadIdx.x; i < 128 * 64; i += blockDim.x) {   // pairs of k
         const int n = i >> 6, k = (i & 63) * 2;
         float v0 = 0.f, v1 = 0.f;
@@ -45,6 +49,7 @@ __global__ void pack_chunks_kernel(const float* __restrict__ img, uint8_t* __res
             v0 = src[(size_t)n * ld + k];
             v1 = src[(size_t)n * ld + k + 1];
         }
+        if (kscale) v0 *= kscale[k], v1 *= kscale[k + 1];
         if (c >= 8 && !KASF_HALF_GELU) {
             *reinterpret_cast<uint32_t*>(dst + tile_off_bf16(n, k)) = pack_bf16(0.5f * v0, 0.5f * v1);
         } else if (c >= 8) {
@@ -84,6 +89,29 @@ __global__ void pack_vectors_kernel(const float* __restrict__ img, uint8_t* __re
             v[V_BV + i] = img[m.Vb + i];
         } else {
             v[V_BMIX + i] = img[m.projb + i];
+        }
+    }
+    if (pm.kind == 2) {
+        // Bone cross-attention with K = (Wk g) xhat + Wk b, V = (Wv g) xhat + Wv b (g, b: limb LayerNorm affine):
+        // the K offset adds the same q . (Wk b) to every key of a query and cancels in the softmax; the V offset passes
+        // through the attention unchanged (the probabilities sum to 1) and becomes part of the projection bias:
+        // b_proj' = b_proj + W_proj (Wv b).  The limb LayerNorm itself is left without affine (gamma 1, beta 0).
+        __shared__ float wvb[D];
+        __syncthreads();
+        for (int o = threadIdx.x; o < D; o += blockDim.x) {
+            const float* wv = img + m.kvw + (size_t)(D + o) * D;
+            float acc = 0.f;
+            for (int k = 0; k < D; ++k) acc = fmaf(wv[k], img[m.nlb + k], acc);
+            wvb[o] = acc;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < D; i += blockDim.x) {
+            const float* wp = img + m.projw + (size_t)i * D;
+            float acc = 0.f;
+            for (int o = 0; o < D; ++o) acc = fmaf(wp[o], wvb[o], acc);
+            v[V_BMIX + i] = img[m.projb + i] + acc;
+            v[V_NLW + i] = 1.f;
+            v[V_NLB + i] = 0.f;
         }
     }
     for (int i = threadIdx.x; i < HID; i += blockDim.x) {

@@ -151,10 +151,23 @@ def attention_mixer(state: State, pre: str, z: Tensor, mode: str, heads: int) ->
     return linear(o, state[pre + "proj.weight"], state[pre + "proj.bias"])
 
 
-def bone_mixer(state: State, pre: str, z: Tensor, zl: Tensor, mode: str, heads: int) -> Tensor:
-    """reference model/modules/bone_crossattention.py:43-62."""
+def bone_mixer(state: State, pre: str, z: Tensor, zl: Tensor, mode: str, heads: int,
+               limb_norm: Optional[tuple] = None) -> Tensor:
+    """reference model/modules/bone_crossattention.py:43-62.
+
+    limb_norm = (xl, gamma, beta) lets the bf16-emulating mode follow the kernels, which fold the limb LayerNorm's
+    affine into the K|V weights (operand = the normalised limb row, rounded to bf16; weight = bf16(W diag(gamma)));
+    the beta term of K cancels in the softmax and the beta term of V is added, in fp32, to the projection bias."""
     C = z.shape[-1]
     q = linear(z, state[pre + "qkv_q.weight"])
+    if EMULATE_BF16 and limb_norm is not None:
+        xl, gamma, beta = limb_norm
+        xhat = F.layer_norm(xl, (C,), None, None, 1e-5)
+        wkv = state[pre + "qkv_kv.weight"]
+        kv = F.linear(_q(xhat), _q(wkv * gamma[None, :]))
+        o = _attend(q, kv[..., :C], kv[..., C:], mode, heads)
+        wp = state[pre + "proj.weight"]
+        return F.linear(_q(o), _q(wp), state[pre + "proj.bias"] + wp @ (wkv[C:] @ beta))
     kv = linear(zl, state[pre + "qkv_kv.weight"])
     o = _attend(q, kv[..., :C], kv[..., C:], mode, heads)
     return linear(o, state[pre + "proj.weight"], state[pre + "proj.bias"])
@@ -227,7 +240,8 @@ def former_module(state: State, pre: str, v: Tensor, xl: Optional[Tensor], kind:
         m = gcn_mixer(state, pre + "mixer.", z, mode, cfg["neighbour_num"])
     else:
         zl = layer_norm(xl, state[pre + "norm1_limb.weight"], state[pre + "norm1_limb.bias"])
-        m = bone_mixer(state, pre + "mixer.", z, zl, mode, cfg["num_heads"])
+        m = bone_mixer(state, pre + "mixer.", z, zl, mode, cfg["num_heads"],
+                       (xl, state[pre + "norm1_limb.weight"], state[pre + "norm1_limb.bias"]))
     if hook:
         hook(pre + "mixer", m)
     v = v + state[pre + "layer_scale_1"] * m

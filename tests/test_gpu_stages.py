@@ -113,6 +113,12 @@ def test_former_module(br, kind, mode, T, B):
         assert err_rows.max().item() <= 4e-3, f"emulated-oracle error {err_rows.max().item()}"
     err_f = ((out - ref).abs().amax(dim=-1).reshape(-1) / upd)
     assert err_f.quantile(0.99).item() <= 3e-2, f"fp32-oracle error {err_f.quantile(0.99).item()}"
+    if kind == "bone":
+        # the path kasf_forward takes: K|V operand from the pre-normalised bf16 limb tiles (one bulk copy per tile)
+        out_lt = _capi.former_module(cfg, blob, 0, kind, mode, v.to(DEV), XL.to(DEV), use_limb_tiles=True).cpu()
+        err_lt = (out_lt - ref_q).abs().amax(dim=-1).reshape(-1) / upd
+        assert err_lt.max().item() <= 4e-3, f"limb-tile path vs emulated oracle {err_lt.max().item()}"
+        assert ((out_lt - out).abs().max() / upd).item() <= 2e-3
 
 
 def test_former_module_in_place_and_default_regime():
