@@ -178,9 +178,94 @@ def save_refinit_fixture():
           "MPJPE", np.mean(mp), "P-MPJPE", np.mean(pmp), "keys", len(rs))
 
 
+def _reference_functions(rel_path, names):
+    """Compile selected top-level functions of a reference file (whose imports are not available here: cv2, lib.*)
+    in a numpy-only namespace.  The function bodies are executed as they are in the read-only checkout."""
+    import ast
+    import copy as _copy
+    src = open(os.path.join(ref_shim.REF, rel_path)).read()
+    tree = ast.parse(src)
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert len(keep) == len(names), (rel_path, names)
+    ns = {"np": np, "copy": _copy}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), rel_path, "exec"), ns)
+    return [ns[n] for n in names]
+
+
+def save_serving_fixture():
+    """demo/demo.py `resample` / `turn_into_clips` and demo/lib/utils.py `normalize_screen_coordinates` /
+    `flip_data` on seeded keypoint tracks of several lengths (rows f2/f3 of SURVEY section 8)."""
+    resample, turn_into_clips = _reference_functions("demo/demo.py", ["resample", "turn_into_clips"])
+    flip_data, normalize = _reference_functions("demo/lib/utils.py", ["flip_data", "normalize_screen_coordinates"])
+    rng = np.random.default_rng(20261017)
+    out = {}
+    # (a length that is a multiple of 27 above 27 makes the reference raise UnboundLocalError at demo.py:156 -- its
+    #  `downsample` is only bound when a clip is stretched; our restatement returns None there)
+    lengths = [5, 27, 28, 40, 100]
+    for n in lengths:
+        kp = (rng.random((1, n, 17, 3)) * np.asarray([1920, 1080, 1.0])).astype(np.float32)
+        clips, down = turn_into_clips(kp, 27)
+        out[f"kp_{n}"] = kp
+        out[f"clips_{n}"] = np.stack(clips)
+        out[f"down_{n}"] = np.asarray(down, np.int64)
+        out[f"norm_{n}"] = normalize(kp, w=1920, h=1080).astype(np.float32)
+    for n, t in [(5, 27), (11, 27), (27, 27), (30, 81), (243, 243)]:
+        out[f"resample_{n}_{t}"] = resample(n, t).astype(np.int64)
+    x = rng.standard_normal((2, 27, 17, 3)).astype(np.float32)
+    out["flip_in"] = x.copy()
+    out["flip_out"] = flip_data(x.copy())
+    out["lengths"] = np.asarray(lengths)
+    np.savez_compressed(os.path.join(OUT, "serving.npz"), **out)
+    print("serving fixture:", len(out), "arrays")
+
+
+def save_clipstore_fixture():
+    """What the reference's test dataset (data/reader/sp_dataset.py:45-92, unmodified, imported) yields for a small
+    directory of synthetic clip pickles in the on-disk format of data/preprocessor/clip_generate_sp.py:48-79."""
+    import pickle
+    import tempfile
+    ref_shim.install()
+    from data.reader.sp_dataset import SportsPose3DDataset
+    rng = np.random.default_rng(7)
+    acts = ["jump", "throw", "jump", "kick", "throw"]
+    with tempfile.TemporaryDirectory() as root:
+        d = os.path.join(root, "clips", "test")
+        os.makedirs(d)
+        recs = []
+        for i, a in enumerate(acts):
+            rec = {"data_input": rng.standard_normal((27, 17, 3)).astype(np.float32),
+                   "data_label": rng.standard_normal((27, 17, 3)).astype(np.float32),
+                   "data_label_scaled": (rng.standard_normal((27, 17, 3)) * 250).astype(np.float32),
+                   "data_factor": (2 + 3 * rng.random(27)).astype(np.float32),
+                   "data_res": (1312, 1216) if i % 2 == 0 else (1216, 1936), "data_action": a, "data_env": "outdoor"}
+            recs.append(rec)
+            with open(os.path.join(d, "%08d.pkl" % i), "wb") as fh:
+                pickle.dump(rec, fh)
+
+        class A(dict):
+            __getattr__ = dict.__getitem__
+        ds = SportsPose3DDataset(A(model_name="KASportsFormer", input_channel_number=3, data_root=root, flip=True,
+                                   clip_set_name="clips"), "test")
+        items = [ds[i] for i in range(len(ds))]
+    out = {"input": np.stack([it[0].numpy() for it in items]), "gt": np.stack([it[1] for it in items]),
+           "factor": np.stack([it[2] for it in items]), "res": np.asarray([it[4] for it in items], np.float32),
+           "actions": np.asarray([it[3] for it in items])}
+    for k in ("data_input", "data_label", "data_label_scaled", "data_factor"):
+        out["rec_" + k] = np.stack([r[k] for r in recs])
+    out["rec_res"] = np.asarray([r["data_res"] for r in recs], np.float32)
+    np.savez_compressed(os.path.join(OUT, "clipstore.npz"), **out)
+    print("clipstore fixture:", len(items), "clips")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if "--io-only" in sys.argv:
+        save_serving_fixture()
+        save_clipstore_fixture()
+        return
+    save_serving_fixture()
+    save_clipstore_fixture()
     save_refinit_fixture()
     save_metrics_fixture()
     # acceptance regime: default init, full depth

@@ -8,3 +8,4 @@ run t1_gemm tests/test_gpu_stages.py -k "gemm_primitive"
 run t2_simple tests/test_gpu_stages.py -k "kinematic or fusion or tables" tests/test_gpu_metrics.py
 run t3_modules tests/test_gpu_stages.py -k "former_module"
 run t4_forward tests/test_gpu_forward.py
+run t5_io tests/test_gpu_io.py
