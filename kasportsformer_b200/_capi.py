@@ -313,7 +313,7 @@ def former_module_phases(cfg, blob, layer, kind, mode, v, XL=None):
     """Run one module with the phase-cycle hook; returns {phase: mean cycles per tile per CTA}."""
     _require_device(v.device)
     out = torch.empty_like(v)
-    prof = torch.zeros(16, dtype=torch.int64, device=v.device)
+    prof = torch.zeros(24, dtype=torch.int64, device=v.device)
     with torch.cuda.device(v.device):
         _check(lib().kasf_former_module_profiled(C.byref(c_config(cfg)), _ptr(blob), layer, KIND[kind], MODE[mode],
                                                  _ptr(v), _ptr(XL), _ptr(out), v.shape[0], _stream(), _ptr(prof)),

@@ -93,7 +93,7 @@ struct ModParams {
     int B, T;
     int ntiles;
     int groups_per_tile;     // temporal: sequences per tile
-    unsigned long long* prof;   // optional [16] per-phase cycle counters (debug/profiling hook), else null
+    unsigned long long* prof;   // optional [24] per-phase cycle counters (debug/profiling hook), else null
     // long sequences (T > 128, split path): scratch in (sequence, frame) row order, row = seq * T + t
     __nv_bfloat16* sq;       // [B*17*T, 128] Q, then the attention output O (in place) | GCN: A_hat z
     __nv_bfloat16* sk;       // [B*17*T, 128] K
@@ -300,6 +300,9 @@ __device__ __forceinline__ void attention_core_impl(uint8_t* sm, int warp, int l
     const int mtiles = (gsize + 15) >> 4;
     const int nkt = (gsize + 7) >> 3;                             // key tiles that hold keys of the group
     const int items = ngroups * HEADS * mtiles;
+    // item / mtiles by multiplication (items < 1024, mtiles <= 8: exact); a runtime integer division per item and
+    // lane cost 8 % of this phase's issue slots
+    const uint32_t inv_mtiles = (65536u + (uint32_t)mtiles - 1u) / (uint32_t)mtiles;
     const int g8 = lane >> 2, t4 = lane & 3, mi = lane >> 3, r8 = lane & 7;
     const float scale = 0.25f * 1.4426950408889634f;              // head_dim^-1/2 * log2(e)
 #pragma unroll 1
@@ -312,7 +315,7 @@ __device__ __forceinline__ void attention_core_impl(uint8_t* sm, int warp, int l
         for (int u = 0; u < U; ++u) {
             live[u] = it0 + u < items;
             const int item = live[u] ? it0 + u : it0;
-            const int gh = item / mtiles;
+            const int gh = GS ? item / mtiles : (int)(((uint32_t)item * inv_mtiles) >> 16);
             mt[u] = item - gh * mtiles, h[u] = gh & (HEADS - 1);
             gr0[u] = (gh >> 3) * gsize;
             const int row = min(gr0[u] + mt[u] * 16 + (mi & 1) * 8 + r8, 127);
@@ -342,10 +345,12 @@ __device__ __forceinline__ void attention_core_impl(uint8_t* sm, int warp, int l
 #pragma unroll
             for (int nt = 0; nt < MAXNT; ++nt) {
                 if (nt < nkt) {
+                    if (nt * 8 + 8 > gsize) {          // only the last key tile of the group can hold keys past its end
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int key = nt * 8 + t4 * 2 + (i & 1);
-                        if (!(key < gsize)) s[u][nt][i] = -INFINITY;
+                        for (int i = 0; i < 4; ++i) {
+                            const int key = nt * 8 + t4 * 2 + (i & 1);
+                            if (!(key < gsize)) s[u][nt][i] = -INFINITY;
+                        }
                     }
                     mx0 = fmaxf(mx0, fmaxf(s[u][nt][0], s[u][nt][1]));
                     mx1 = fmaxf(mx1, fmaxf(s[u][nt][2], s[u][nt][3]));

@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -22,6 +23,44 @@ __device__ __forceinline__ float gelu2(float v) {
     const float v2 = v * v;
     const float pl = fmaf(v2, fmaf(v2, -0.0003828259195935171f, 0.03722352208203997f), 0.7972238404651819f);
     return fmaf(v, tanh_fast(v * pl), v);
+}
+
+// ---- packed-half variants (what kasf_module.cu runs since r01p) ----
+__device__ __forceinline__ __half2 u2h(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ uint32_t h2u(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ __half2 arg_h2(__half2 v) {
+    const __half2 s = __hmin2(__hmul2(v, v), __float2half2_rn(48.5f));
+    const __half2 p = __hfma2(s, __hfma2(s, __float2half2_rn(-0.0003828259195935171f), __float2half2_rn(0.03722352208203997f)),
+                              __float2half2_rn(0.7972238404651819f));
+    return __hmul2(v, p);
+}
+__device__ __forceinline__ __half2 tanh_h2(__half2 w) {
+    uint32_t t;
+    asm volatile("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(h2u(w)));
+    return u2h(t);
+}
+// 2*GELU(v) = (v + |v|) - G(min(|v|, 4)),  G(a) = a erfc(a / sqrt 2) as a degree-9 polynomial in t = a/2 - 1:
+// FMA pipe only, no cancellation for negative v
+__device__ __forceinline__ __half2 gelu2_poly_h2(__half2 v) {
+    const __half2 a0 = __habs2(v);
+    const __half2 a = __hmin2(a0, __float2half2_rn(4.0f));
+    const __half2 t = __hfma2(a, __float2half2_rn(0.5f), __float2half2_rn(-1.0f));
+    __half2 g = __float2half2_rn(5.194650522e-02f);
+    g = __hfma2(g, t, __float2half2_rn(4.162358846e-02f));
+    g = __hfma2(g, t, __float2half2_rn(-2.858623454e-01f));
+    g = __hfma2(g, t, __float2half2_rn(3.757820403e-02f));
+    g = __hfma2(g, t, __float2half2_rn(5.746606458e-01f));
+    g = __hfma2(g, t, __float2half2_rn(-6.049317139e-01f));
+    g = __hfma2(g, t, __float2half2_rn(3.410460008e-04f));
+    g = __hfma2(g, t, __float2half2_rn(4.350995496e-01f));
+    g = __hfma2(g, t, __float2half2_rn(-3.409467094e-01f));
+    g = __hfma2(g, t, __float2half2_rn(9.094493380e-02f));
+    return __hsub2(__hadd2(v, a0), g);
 }
 
 // VAR 0: as in kasf_module.cu (8-element groups as the compiler schedules them)
@@ -54,6 +93,35 @@ __global__ void __launch_bounds__(512, 1) k(const float* in, const float* bias, 
                 pk.z = pack_bf16(gelu2(acc[c8 * 8 + 4] + bb.x), gelu2(acc[c8 * 8 + 5] + bb.y));
                 pk.w = pack_bf16(gelu2(acc[c8 * 8 + 6] + bb.z), gelu2(acc[c8 * 8 + 7] + bb.w));
                 *reinterpret_cast<uint4*>(dst + tile_off_bf16(row, part * COLS + c8 * 8)) = pk;
+            }
+        } else if (VAR == 2 || VAR == 3) {
+            // packed half: groups of 8 columns = 4 pairs; VAR 3 sends pair 3 of every group through the FMA-pipe polynomial
+            const uint4* b1h = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(vb) + c * 128 + part * COLS);
+            constexpr int NM = VAR == 3 ? 3 : 4;       // pairs per group on the MUFU path
+            __half2 v[2][4], w[2][4];
+            auto stage1 = [&](int g, int s) {
+                const uint4 bh = b1h[g];
+                v[s][0] = __hadd2(u2h(pack_f16(acc[g * 8 + 0], acc[g * 8 + 1])), u2h(bh.x));
+                v[s][1] = __hadd2(u2h(pack_f16(acc[g * 8 + 2], acc[g * 8 + 3])), u2h(bh.y));
+                v[s][2] = __hadd2(u2h(pack_f16(acc[g * 8 + 4], acc[g * 8 + 5])), u2h(bh.z));
+                v[s][3] = __hadd2(u2h(pack_f16(acc[g * 8 + 6], acc[g * 8 + 7])), u2h(bh.w));
+#pragma unroll
+                for (int i = 0; i < NM; ++i) w[s][i] = arg_h2(v[s][i]);
+            };
+            stage1(0, 0);
+#pragma unroll
+            for (int g = 0; g < COLS / 8; ++g) {
+                const int s = g & 1;
+                __half2 t[4], r[4];
+#pragma unroll
+                for (int i = 0; i < NM; ++i) t[i] = tanh_h2(w[s][i]);
+                if (VAR == 3) r[3] = gelu2_poly_h2(v[s][3]);
+                if (g + 1 < COLS / 8) stage1(g + 1, s ^ 1);
+#pragma unroll
+                for (int i = 0; i < NM; ++i) r[i] = __hfma2(v[s][i], t[i], v[s][i]);
+                uint4 pk;
+                pk.x = h2u(r[0]), pk.y = h2u(r[1]), pk.z = h2u(r[2]), pk.w = h2u(r[3]);
+                *reinterpret_cast<uint4*>(dst + tile_off_bf16(row, part * COLS + g * 8)) = pk;
             }
         } else {
             float v[2][G], w[2][G];
@@ -124,6 +192,8 @@ int main() {
     run<1, 8, 64>("pipelined G=8 (8 warps)");
     run<1, 16, 64>("pipelined G=16 (8 warps)");
     run<1, 32, 64>("pipelined G=32 (8 warps)");
+    run<2, 8, 64>("packed half, MUFU tanh (8 warps)");
+    run<3, 8, 64>("packed half, 3 of 4 pairs MUFU + 1 poly (8 warps)");
     run<0, 8, 32>("as compiled (16 warps, 32 cols/thread)");
     run<1, 16, 32>("pipelined G=16 (16 warps)");
     return 0;

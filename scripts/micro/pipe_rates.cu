@@ -12,6 +12,7 @@ constexpr int ILP = 8, ITERS = 2048;
 template <int OP>
 __global__ void k(float* out, long long* cyc, float seed) {
     float v[ILP];
+    float aux = 0.f;
 #pragma unroll
     for (int i = 0; i < ILP; ++i) v[i] = seed + 0.001f * (threadIdx.x + i);
     __syncthreads();
@@ -49,6 +50,45 @@ __global__ void k(float* out, long long* cyc, float seed) {
                 v[i] = fmaf(x, t, x);
             }
             if (OP == 6) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(v[i]));
+            if (OP == 8) {   // HFMA2 alone
+                unsigned u = __float_as_uint(v[i]);
+                asm volatile("fma.rn.f16x2 %0, %0, %1, %1;" : "+r"(u) : "r"(0x3c003c00u));
+                v[i] = __uint_as_float(u);
+            }
+            if (OP == 9) {   // MUFU.TANH + 4 FFMA (independent)
+                asm volatile("tanh.approx.f32 %0, %0;" : "+f"(v[i]));
+                float a = seed, b = seed + 1.f, c = seed + 2.f, d = seed + 3.f;
+                asm volatile("fma.rn.f32 %0, %0, %0, %0;\n\tfma.rn.f32 %1, %1, %1, %1;\n\tfma.rn.f32 %2, %2, %2, %2;\n\tfma.rn.f32 %3, %3, %3, %3;"
+                             : "+f"(a), "+f"(b), "+f"(c), "+f"(d));
+                aux += a + b + c + d;
+            }
+            if (OP == 10) {  // MUFU.TANH + 4 HFMA2 (independent)
+                asm volatile("tanh.approx.f32 %0, %0;" : "+f"(v[i]));
+                unsigned a = 0x3c003c00u + i, b = a + 1, c = a + 2, d = a + 3;
+                asm volatile("fma.rn.f16x2 %0, %0, %0, %0;\n\tfma.rn.f16x2 %1, %1, %1, %1;\n\tfma.rn.f16x2 %2, %2, %2, %2;\n\tfma.rn.f16x2 %3, %3, %3, %3;"
+                             : "+r"(a), "+r"(b), "+r"(c), "+r"(d));
+                aux += __uint_as_float(a ^ b ^ c ^ d);
+            }
+            if (OP == 11) {  // MUFU.TANH + 1 F2FP (independent)
+                asm volatile("tanh.approx.f32 %0, %0;" : "+f"(v[i]));
+                unsigned u;
+                asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(seed + i), "f"(seed));
+                aux += __uint_as_float(u);
+            }
+            if (OP == 12) {  // F2FP f16x2 alone
+                unsigned u;
+                asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(v[i]), "f"(seed));
+                v[i] = __uint_as_float(u | 0x3c000000u);
+            }
+            if (OP == 13) {  // MUFU.TANH.F16 x2 (tanh.approx.f16x2) + 4 HFMA2
+                unsigned u = __float_as_uint(v[i]);
+                asm volatile("tanh.approx.f16x2 %0, %0;" : "+r"(u));
+                v[i] = __uint_as_float(u);
+                unsigned a = 0x3c003c00u + i, b = a + 1, c = a + 2, d = a + 3;
+                asm volatile("fma.rn.f16x2 %0, %0, %0, %0;\n\tfma.rn.f16x2 %1, %1, %1, %1;\n\tfma.rn.f16x2 %2, %2, %2, %2;\n\tfma.rn.f16x2 %3, %3, %3, %3;"
+                             : "+r"(a), "+r"(b), "+r"(c), "+r"(d));
+                aux += __uint_as_float(a ^ b ^ c ^ d);
+            }
             if (OP == 7) v[i] = fmaf(v[i], seed, 0.5f);
         }
     }
@@ -56,6 +96,7 @@ __global__ void k(float* out, long long* cyc, float seed) {
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < ILP; ++i) s += v[i];
+    s += aux;
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
@@ -89,6 +130,12 @@ int main() {
     run<3>("F2FP bf16x2 pack (+LOP)", 2);
     run<6>("MUFU.RCP", 1);
     run<7>("FFMA", 1);
+    run<8>("HFMA2", 1);
+    run<12>("F2FP f16x2", 1);
+    run<9>("MUFU.TANH + 4 FFMA", 5);
+    run<10>("MUFU.TANH + 4 HFMA2", 5);
+    run<11>("MUFU.TANH + F2FP", 2);
+    run<13>("tanh.f16x2 + 4 HFMA2", 7);
     run<4>("GELU seq (tanh MUFU)", 7);
     run<5>("GELU seq (FMA-pipe poly)", 13);
     return 0;

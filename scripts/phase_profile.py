@@ -15,7 +15,7 @@ for kind in ("attention", "graph", "bone"):
     for mode in ("spatial", "temporal"):
         _capi.former_module(cfg, blob, 0, kind, mode, v, xl)      # warm
         ph, tiles = _capi.former_module_phases(cfg, blob, 0, kind, mode, v, xl)
-        tot = sum(x for k, x in ph.items() if not k.startswith("gather_"))
+        tot = sum(x for k, x in ph.items() if not k.startswith("mmawarp_"))
         out[f"{kind}_{mode}"] = {"tiles": tiles, "cycles_per_tile": round(tot), **{k: round(x) for k, x in ph.items() if x > 0}}
         print(kind, mode, "tiles", tiles, "cyc/tile", round(tot), {k: round(x) for k, x in ph.items() if x > 0})
 json.dump(out, open("gpurun_out/phases.json", "w"), indent=1)
