@@ -11,7 +11,7 @@ exchange of the path).  Rank 0 prints ONE JSON line.
 
   value ...... whole-job clips/s with the inputs already resident in HBM (CUDA events, max over ranks)
   e2e ........ the same through the drop-in nn.Module with HOST buffers: pinned x -> H2D -> forward -> D2H y
-  roofline ... the fused FormerModule kernels (156 of the 184 launches per forward, >95 % of the time):
+  roofline ... the fused FormerModule kernels (156 of the 186 launches per forward, >95 % of the time):
                algorithmic FLOPs / per-launch device time measured with CUDA events between
                the launches of the timed steps, against the measured sustained bf16 peak
   cpu_baseline oracle port of the reference forward timed on the host cores (bounded sample)
@@ -258,9 +258,9 @@ def run_ours(args):
             if tj["batch"] == B and tj["frames"] == T:
                 per = [v["dram_read_bytes"] + v["dram_write_bytes"] for v in tj["per_launch"].values()]
                 traffic, traffic_src = sum(per) / len(per), tj["capture"]
-        # algorithmic HBM bytes per launch: 512 B read + 512 B written per token (+ 512 B of the limb stream in the
+        # algorithmic HBM bytes per launch: 512 B read + 512 B written per token (+ 256 B of the bf16 limb tile in the
         # two bone modules): mean over the six instantiations
-        alg_bytes = tokens * 512 * (2 * 4 + 3 * 2) / 6
+        alg_bytes = tokens * (512 * 2 * 6 + 256 * 2) / 6
         out = {
             "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

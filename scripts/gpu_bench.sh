@@ -5,8 +5,8 @@ python __graft_entry__.py smoke > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke ex
 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench exit $?"
 tail -n 5 gpurun_out/bench_$TAG.err; cat gpurun_out/bench_$TAG.json
 if [ "$2" == "ncu" ]; then
-  # launch list of one whole step: skip weight packing (53) + 3 warm-up steps (185 each)
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 608 -c 190 --csv \
+  # launch list of one whole step: skip weight packing (53) + 3 warm-up steps (187 launches each)
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 614 -c 190 --csv \
       --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu1_$TAG.log 2>&1
   echo "ncu launch list exit $?"
   # full capture of the six FormerModule kernels of one layer (after the warm-up forwards)

@@ -4,12 +4,29 @@ FormerModule kernel (source-line ranges of kasf_module.cu), with the dominant st
 usage: ncu_phases.py dump.csv [kernel-substring]"""
 import csv, sys
 csv.field_size_limit(1 << 30)
-BUCKETS = [  # (name, first line, last line) in kasf_module.cu
-    ("gelu helpers", 104, 152), ("ln_stats", 202, 222), ("ln_write", 223, 255), ("attention core", 256, 430),
-    ("similarity mma", 431, 514), ("similarity topk", 515, 576), ("gather/read_staged", 578, 634),
-    ("arrive", 635, 648), ("setup", 650, 688), ("producer+mma warps", 689, 775), ("limb / load", 776, 853),
-    ("qkv drain", 854, 904), ("gcn aggregation", 905, 987), ("mixer epilogue + ln2", 988, 1036),
-    ("mlp epilogue", 1037, 1118), ("out epilogue", 1119, 1160)]
+import os
+# phase = source-line range of kasf_module.cu, located by the first line containing a marker (the source must be the
+# one the capture was built from)
+MARKERS = [("gelu helpers", "TWICE the erf-GELU"), ("tile helpers", "fp32 [128][128] tile with XOR-swizzled"),
+           ("ln_stats", "void ln_stats("), ("ln_write", "template <bool Z_TO_AUX>"),
+           ("attention core", "warp-level MMAs"), ("similarity mma", "temporal adjacency"),
+           ("similarity topk", "a row is spread over the 4 lanes of a quad"), ("tile geometry", "tile geometry"),
+           ("gather/read_staged", "Row gather of a tile, issued by the compute warps"), ("arrive", "void warp_arrive("),
+           ("setup", "__global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel"),
+           ("producer+mma warps", "service warpgroup (hands its registers"), ("limb / load + ln1", "compute warps ====="),
+           ("qkv drain", "Q,K,V: TMEM -> bf16 smem"), ("attention call", "attention_core<MODE, TC>(sm"),
+           ("gcn mixer", "GCN mixer ====="), ("mixer epilogue + ln2", "x1 = x + ls1 * mixer"),
+           ("mlp epilogue", "MLP epilogues: hidden chunk c"), ("out epilogue", "B1|B2 are free: request the next tile"),
+           ("kernel tail", "tc_fence_before();\n    __syncthreads();\n    if (warp == 0) tmem_dealloc"),
+           ("launch + split path", "static int launch_one(")]
+_src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "kasportsformer_b200", "csrc", "kasf_module.cu")).read()
+_starts = []
+for name, mark in MARKERS:
+    i = _src.find(mark)
+    if i >= 0:
+        _starts.append((_src.count("\n", 0, i) + 1, name))
+_starts.sort()
+BUCKETS = [(n, a, (_starts[i + 1][0] - 1) if i + 1 < len(_starts) else 10 ** 9) for i, (a, n) in enumerate(_starts)]
 want = sys.argv[2] if len(sys.argv) > 2 else ""
 fname, kern, hdr = "", "", None
 agg = {}
