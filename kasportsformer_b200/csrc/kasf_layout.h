@@ -161,9 +161,10 @@ constexpr int V_LS1 = 0, V_LS2 = 128, V_N1W = 256, V_N1B = 384, V_NLW = 512, V_N
               V_N2B = 896, V_BMIX = 1024 /* proj bias | U bias */, V_BV = 1152, V_B1 = 1280, V_B2 = 1792,
               V_BNS = 1920 /* [256] */, V_BNT = 2176 /* [256] */,
               V_B1H = 2560 /* fc1 bias as 512 fp16 values (256 floats) for the packed-half GELU epilogue */,
-              V_FLOATS = 2816;
-constexpr size_t MOD_VEC_BYTES = V_FLOATS * 4;                                  // 11264
-constexpr size_t MOD_BYTES = MOD_VEC_BYTES + MOD_CHUNKS * CHUNK_BYTES;          // 404480
+              V_BQ = 2816 /* [128] query bias W_q beta_1 (attention / bone: LN1's affine is folded into the weights) */,
+              V_FLOATS = 2944;
+constexpr size_t MOD_VEC_BYTES = V_FLOATS * 4;                                  // 11776
+constexpr size_t MOD_BYTES = MOD_VEC_BYTES + MOD_CHUNKS * CHUNK_BYTES;          // 404992
 constexpr size_t FUSION_BYTES = 5120;                                            // W[3][384], b[3] fp32
 constexpr size_t LAYER_BYTES = 6 * MOD_BYTES + FUSION_BYTES;
 // chunk order inside a module (natural order; the kernel's producer walks its own sequence):

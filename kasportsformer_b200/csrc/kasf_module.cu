@@ -27,7 +27,7 @@
 // Shared memory map (bytes):   AUX    K|V bf16 / z fp32 / MLP hidden tiles                 65536
 //                              ATILE  bf16 A operand [128 x 128] (also Q, attention output)  32768
 //                              RING   3 x weight chunk [128 x 128] bf16                      98304
-//                              VEC    the module's fp32 vectors (LN, layer scale, biases)     11264
+//                              VEC    the module's fp32 vectors (LN, layer scale, biases)     11776
 //                              LN partials, adjacency bit masks, degrees, barriers
 // Tensor memory columns:       0..127 Q -> mixer output -> hidden chunk 0 | 128..255 K -> hidden chunk 1
 //                              256..383 V -> fc2 accumulator             | 384..511 residual rows X
@@ -67,7 +67,7 @@ constexpr uint32_t SM_RSD = SM_ROWSUM + 512;          // f32 [128]  degree^-1/2 
 constexpr uint32_t SM_BARS = SM_RSD + 512;
 constexpr uint32_t SM_TOTAL = SM_BARS + 256;
 static_assert(SM_TOTAL <= 232448, "shared memory budget");
-static_assert(MOD_VEC_BYTES == 11264, "vector block size");
+static_assert(MOD_VEC_BYTES == 11776, "vector block size");
 
 constexpr uint32_t TM_MIX = 0, TM_K = 128, TM_V = 256, TM_X = 384;   // mixer phase (Q lives at TM_MIX)
 constexpr uint32_t TM_H0 = 0, TM_H1 = 128, TM_OUT = 256;            // MLP phase
@@ -899,6 +899,16 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                         uint32_t acc[32];
                         tmem_ld32(e.tbase + qkv * 128 + e.half * 64 + b * 32, acc);
                         tmem_ld_wait();
+                        if (qkv == 0) {                    // query bias W_q beta_1 (LN1's affine lives in the weights)
+#pragma unroll
+                            for (int c4 = 0; c4 < 8; ++c4) {
+                                const float4 bq = *reinterpret_cast<const float4*>(vec + V_BQ + e.half * 64 + b * 32 + c4 * 4);
+                                acc[c4 * 4 + 0] = __float_as_uint(__uint_as_float(acc[c4 * 4 + 0]) + bq.x);
+                                acc[c4 * 4 + 1] = __float_as_uint(__uint_as_float(acc[c4 * 4 + 1]) + bq.y);
+                                acc[c4 * 4 + 2] = __float_as_uint(__uint_as_float(acc[c4 * 4 + 2]) + bq.z);
+                                acc[c4 * 4 + 3] = __float_as_uint(__uint_as_float(acc[c4 * 4 + 3]) + bq.w);
+                            }
+                        }
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             uint4 pk;
@@ -1311,6 +1321,11 @@ __global__ void __launch_bounds__(256, 1) long_pre_kernel(const ModParams p) {
             uint32_t acc[32];
             tmem_ld32(e.tbase + qkv * 128 + e.half * 64 + b * 32, acc);
             tmem_ld_wait();
+            if (qkv == 0) {                                // query bias W_q beta_1
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    acc[i] = __float_as_uint(__uint_as_float(acc[i]) + vec[V_BQ + e.half * 64 + b * 32 + i]);
+            }
             if (row_ok) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {

@@ -41,7 +41,10 @@ __global__ void pack_chunks_kernel(const float* __restrict__ img, uint8_t* __res
     // bone K|V projections: the limb LayerNorm's gamma is folded into the weight columns, so that the operand is the
     // layer-independent normalised limb row (computed once per forward, see limb_tiles_kernel); beta goes to the
     // output-projection bias (pack_vectors_kernel)
-    const float* kscale = (pm.kind == 2 && (c == 1 || c == 2)) ? img + pm.img.nlw : nullptr;
+    // likewise LN1's gamma is folded into the Q|K|V (attention) / Q (bone) weight columns: their operand is the
+    // normalised stream row, which a producer kernel can hand over ready-made (see xhat tiles in kasf_module.cu)
+    const float* kscale = (pm.kind == 2 && (c == 1 || c == 2)) ? img + pm.img.nlw
+                          : ((pm.kind == 0 && c < 3) || (pm.kind == 2 && c == 0)) ? img + pm.img.n1w : nullptr;
     for (int i = threadIdx.x; i < 128 * 64; i += blockDim.x) {   // pairs of k
         const int n = i >> 6, k = (i & 63) * 2;
         float v0 = 0.f, v1 = 0.f;
@@ -89,6 +92,36 @@ __global__ void pack_vectors_kernel(const float* __restrict__ img, uint8_t* __re
             v[V_BV + i] = img[m.Vb + i];
         } else {
             v[V_BMIX + i] = img[m.projb + i];
+        }
+    }
+    if (pm.kind == 0 || pm.kind == 2) {
+        // LN1's affine (g1, b1) folded into the projections of the stream rows: q = (Wq g1) xhat + Wq b1 keeps its
+        // offset as an explicit query bias (V_BQ, added when Q is drained); the K offset cancels in the softmax; the V
+        // offset (self-attention only) joins the projection bias below.  LN1 itself is left without affine.
+        const float* wq = pm.kind == 0 ? img + m.qkvw : img + m.qw;
+        for (int o = threadIdx.x; o < D; o += blockDim.x) {
+            float acc = 0.f;
+            for (int k = 0; k < D; ++k) acc = fmaf(wq[(size_t)o * D + k], img[m.n1b + k], acc);
+            v[V_BQ + o] = acc;
+            v[V_N1W + o] = 1.f;
+            v[V_N1B + o] = 0.f;
+        }
+    }
+    if (pm.kind == 0) {
+        __shared__ float wvb0[D];
+        __syncthreads();
+        for (int o = threadIdx.x; o < D; o += blockDim.x) {
+            const float* wv = img + m.qkvw + (size_t)(2 * D + o) * D;
+            float acc = 0.f;
+            for (int k = 0; k < D; ++k) acc = fmaf(wv[k], img[m.n1b + k], acc);
+            wvb0[o] = acc;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < D; i += blockDim.x) {
+            const float* wp = img + m.projw + (size_t)i * D;
+            float acc = 0.f;
+            for (int o = 0; o < D; ++o) acc = fmaf(wp[o], wvb0[o], acc);
+            v[V_BMIX + i] = img[m.projb + i] + acc;
         }
     }
     if (pm.kind == 2) {

@@ -143,23 +143,41 @@ def _attend(q: Tensor, k: Tensor, v: Tensor, mode: str, heads: int) -> Tensor:
     return o.permute(0, 2, 3, 1, 4).reshape(B, T, J, C)
 
 
-def attention_mixer(state: State, pre: str, z: Tensor, mode: str, heads: int) -> Tensor:
-    """reference model/modules/selfattention.py:44-60."""
+def attention_mixer(state: State, pre: str, z: Tensor, mode: str, heads: int, norm: Optional[tuple] = None) -> Tensor:
+    """reference model/modules/selfattention.py:44-60.
+
+    norm = (x, gamma, beta) lets the bf16-emulating mode follow the kernels, which fold LN1's affine into the Q|K|V
+    weights: operand = the normalised row rounded to bf16, weight = bf16(W diag(gamma)), explicit fp32 query bias
+    W_q beta; the beta term of K cancels in the softmax, the one of V joins the projection bias."""
     C = z.shape[-1]
+    if EMULATE_BF16 and norm is not None:
+        x, gamma, beta = norm
+        xhat = F.layer_norm(x, (C,), None, None, 1e-5)
+        w = state[pre + "qkv.weight"]
+        qkv = F.linear(_q(xhat), _q(w * gamma[None, :]))
+        q = qkv[..., :C] + w[:C] @ beta
+        o = _attend(q, qkv[..., C:2 * C], qkv[..., 2 * C:], mode, heads)
+        wp = state[pre + "proj.weight"]
+        return F.linear(_q(o), _q(wp), state[pre + "proj.bias"] + wp @ (w[2 * C:] @ beta))
     qkv = linear(z, state[pre + "qkv.weight"])
     o = _attend(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], mode, heads)
     return linear(o, state[pre + "proj.weight"], state[pre + "proj.bias"])
 
 
 def bone_mixer(state: State, pre: str, z: Tensor, zl: Tensor, mode: str, heads: int,
-               limb_norm: Optional[tuple] = None) -> Tensor:
+               limb_norm: Optional[tuple] = None, norm: Optional[tuple] = None) -> Tensor:
     """reference model/modules/bone_crossattention.py:43-62.
 
     limb_norm = (xl, gamma, beta) lets the bf16-emulating mode follow the kernels, which fold the limb LayerNorm's
     affine into the K|V weights (operand = the normalised limb row, rounded to bf16; weight = bf16(W diag(gamma)));
     the beta term of K cancels in the softmax and the beta term of V is added, in fp32, to the projection bias."""
     C = z.shape[-1]
-    q = linear(z, state[pre + "qkv_q.weight"])
+    if EMULATE_BF16 and norm is not None:      # LN1's affine folded into W_q, explicit query bias (see attention_mixer)
+        x, gamma, beta = norm
+        wq = state[pre + "qkv_q.weight"]
+        q = F.linear(_q(F.layer_norm(x, (C,), None, None, 1e-5)), _q(wq * gamma[None, :])) + wq @ beta
+    else:
+        q = linear(z, state[pre + "qkv_q.weight"])
     if EMULATE_BF16 and limb_norm is not None:
         xl, gamma, beta = limb_norm
         xhat = F.layer_norm(xl, (C,), None, None, 1e-5)
@@ -235,13 +253,15 @@ def former_module(state: State, pre: str, v: Tensor, xl: Optional[Tensor], kind:
     """reference model/KASportsFormer.py:103-118 (use_layer_scale=True path)."""
     z = layer_norm(v, state[pre + "norm1.weight"], state[pre + "norm1.bias"])
     if kind == "attention":
-        m = attention_mixer(state, pre + "mixer.", z, mode, cfg["num_heads"])
+        m = attention_mixer(state, pre + "mixer.", z, mode, cfg["num_heads"],
+                            (v, state[pre + "norm1.weight"], state[pre + "norm1.bias"]))
     elif kind == "graph":
         m = gcn_mixer(state, pre + "mixer.", z, mode, cfg["neighbour_num"])
     else:
         zl = layer_norm(xl, state[pre + "norm1_limb.weight"], state[pre + "norm1_limb.bias"])
         m = bone_mixer(state, pre + "mixer.", z, zl, mode, cfg["num_heads"],
-                       (xl, state[pre + "norm1_limb.weight"], state[pre + "norm1_limb.bias"]))
+                       (xl, state[pre + "norm1_limb.weight"], state[pre + "norm1_limb.bias"]),
+                       (v, state[pre + "norm1.weight"], state[pre + "norm1.bias"]))
     if hook:
         hook(pre + "mixer", m)
     v = v + state[pre + "layer_scale_1"] * m
