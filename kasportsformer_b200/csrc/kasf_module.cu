@@ -436,6 +436,21 @@ __device__ __forceinline__ void attention_core(uint8_t* sm, int warp, int lane, 
     else attention_core_impl<16, 1, 0>(sm, warp, lane, gsize, nrows);
 }
 
+// ---------------------------------------------------------------------------------------------- top-4 networks
+__device__ __forceinline__ void cmpx(float& a, float& b) {   // a >= b afterwards
+    const float hi = fmaxf(a, b), lo = fminf(a, b);
+    a = hi, b = lo;
+}
+__device__ __forceinline__ void sort4_desc(float (&c)[4]) {
+    cmpx(c[0], c[1]), cmpx(c[2], c[3]), cmpx(c[0], c[2]), cmpx(c[1], c[3]), cmpx(c[1], c[2]);
+}
+// a <- the four largest of (a U b), sorted descending; a and b sorted descending (duplicates kept)
+__device__ __forceinline__ void merge_top4(float (&a)[4], const float (&b)[4]) {
+    float c[4] = {fmaxf(a[0], b[3]), fmaxf(a[1], b[2]), fmaxf(a[2], b[1]), fmaxf(a[3], b[0])};   // bitonic
+    cmpx(c[0], c[2]), cmpx(c[1], c[3]), cmpx(c[0], c[1]), cmpx(c[2], c[3]);
+    a[0] = c[0], a[1] = c[1], a[2] = c[2], a[3] = c[3];
+}
+
 // ---------------------------------------------------------------------------------------------- temporal adjacency
 // S = z z^T per sequence to fp32 accuracy on tensor cores (3xTF32: the operand is split into the 19 bits the
 // tensor core reads and the exact fp32 remainder; hi*hi + hi*lo + lo*hi), then per row the 4th largest value
@@ -534,28 +549,33 @@ __device__ __forceinline__ void similarity_topk_impl(uint8_t* sm, int warp, int 
 #pragma unroll
                 for (int i = 0; i < 2; ++i)
                     v[nt][i] = (nt < nkt && nt * 8 + t4 * 2 + i < T) ? s[nt][hrow * 2 + i] : -INFINITY;
-            float thr = 0.f;
-#ifdef KASF_DBG_SKIP_TOPK
-            for (int it = 0; it < 0; ++it) {
-#else
-#pragma unroll 1
-            for (int it = 0; it < 4; ++it) {
-#endif
-                float lm = -INFINITY;
+            // 4th largest value of the row with multiplicity (torch.topk + ">=", graph.py:109-111), by sorting
+            // networks: every lane reduces its 2 MAXNT values to a sorted top-4 (groups of four: 5 compare-exchanges,
+            // then a bitonic top-4 merge per further group), the quad merges its four lists with two shuffle rounds.
+            // (Four rounds of "quad maximum, remove one instance" cost 4.7k cycles per tile.)
+            float best[4];
 #pragma unroll
-                for (int nt = 0; nt < MAXNT; ++nt) lm = fmaxf(lm, fmaxf(v[nt][0], v[nt][1]));
-                thr = fmaxf(lm, __shfl_xor_sync(0xffffffffu, lm, 1));
-                thr = fmaxf(thr, __shfl_xor_sync(0xffffffffu, thr, 2));
-                const unsigned owners = (__ballot_sync(0xffffffffu, lm == thr) >> (g8 * 4)) & 0xfu;
-                if (t4 == __ffs(owners) - 1) {          // remove exactly one instance of the maximum
-                    bool done = false;
+            for (int g4 = 0; g4 < MAXNT / 2; ++g4) {
+                float c[4] = {v[2 * g4][0], v[2 * g4][1], v[2 * g4 + 1][0], v[2 * g4 + 1][1]};
+                sort4_desc(c);
+                if (g4 == 0) {
 #pragma unroll
-                    for (int nt = 0; nt < MAXNT; ++nt)
-#pragma unroll
-                        for (int i = 0; i < 2; ++i)
-                            if (!done && v[nt][i] == thr) v[nt][i] = -INFINITY, done = true;
+                    for (int i = 0; i < 4; ++i) best[i] = c[i];
+                } else {
+                    merge_top4(best, c);
                 }
             }
+            {
+                float o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o[i] = __shfl_xor_sync(0xffffffffu, best[i], 1);
+                merge_top4(best, o);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o[i] = __shfl_xor_sync(0xffffffffu, best[i], 2);
+                // the 4th largest of the union of two sorted top-4 lists: min_i max(a_i, b_{3-i})
+                best[0] = fminf(fminf(fmaxf(best[0], o[3]), fmaxf(best[1], o[2])), fminf(fmaxf(best[2], o[1]), fmaxf(best[3], o[0])));
+            }
+            const float thr = best[0];
             // adjacency bits of this row: key 8 nt + 2 t4 + i
             const int row = m0 + g8 + hrow * 8;
             int deg = 0;
