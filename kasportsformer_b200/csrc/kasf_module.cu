@@ -1524,68 +1524,67 @@ __global__ void __launch_bounds__(256, 1) long_gcn_kernel(const ModParams p) {
         for (int nt = 0; nt < 32; ++nt)
 #pragma unroll
             for (int i = 0; i < 4; ++i) s[nt][i] = 0.f;
+        // K = 128 in eight double steps of 16 columns, 128-bit operand loads with the k permutation of
+        // similarity_topk_impl (lane t4 takes columns 16 d + 4 t4 .. + 3); the key rows 8 nt + g8 share the swizzle
+        // phase g8, so every B address is one base plus an immediate
+        const uint32_t zrow_a = LG_Z + ra * 512 + ((t4 ^ (ra & 7)) << 4);
+        const uint32_t zrow_b = LG_Z + rb * 512 + ((t4 ^ (rb & 7)) << 4);
+        const uint32_t zrow_j = LG_Z + g8 * 512 + ((t4 ^ g8) << 4);
+        auto split = [](float v, uint32_t& hi, uint32_t& lo) {
+            hi = __float_as_uint(v) & 0xffffe000u;
+            lo = __float_as_uint(v - __uint_as_float(hi));
+        };
 #pragma unroll 1
-        for (int ks = 0; ks < 16; ++ks) {
-            float av[4];
-            av[0] = *reinterpret_cast<const float*>(sm + LG_Z + f32_off(ra, 2 * ks) + t4 * 4);
-            av[1] = *reinterpret_cast<const float*>(sm + LG_Z + f32_off(rb, 2 * ks) + t4 * 4);
-            av[2] = *reinterpret_cast<const float*>(sm + LG_Z + f32_off(ra, 2 * ks + 1) + t4 * 4);
-            av[3] = *reinterpret_cast<const float*>(sm + LG_Z + f32_off(rb, 2 * ks + 1) + t4 * 4);
-            uint32_t ah[4], al[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                ah[i] = __float_as_uint(av[i]) & 0xffffe000u;
-                al[i] = __float_as_uint(av[i] - __uint_as_float(ah[i]));
-            }
+        for (int d = 0; d < 8; ++d) {
+            const uint32_t off = (d >> 1) * 128, flip = (d & 1) << 6;
+            const float4 fa = *reinterpret_cast<const float4*>(sm + ((zrow_a + off) ^ flip));
+            const float4 fb = *reinterpret_cast<const float4*>(sm + ((zrow_b + off) ^ flip));
+            uint32_t ah[2][4], al[2][4];
+            split(fa.x, ah[0][0], al[0][0]), split(fb.x, ah[0][1], al[0][1]), split(fa.y, ah[0][2], al[0][2]), split(fb.y, ah[0][3], al[0][3]);
+            split(fa.z, ah[1][0], al[1][0]), split(fb.z, ah[1][1], al[1][1]), split(fa.w, ah[1][2], al[1][2]), split(fb.w, ah[1][3], al[1][3]);
+            const uint8_t* bj = sm + ((zrow_j + off) ^ flip);
 #pragma unroll
             for (int nt = 0; nt < 32; ++nt) {
                 if (nt < nkt) {
-                    const int rj = 8 * nt + g8;
-                    const float b0 = *reinterpret_cast<const float*>(sm + LG_Z + f32_off(rj, 2 * ks) + t4 * 4);
-                    const float b1 = *reinterpret_cast<const float*>(sm + LG_Z + f32_off(rj, 2 * ks + 1) + t4 * 4);
-                    const uint32_t bh0 = __float_as_uint(b0) & 0xffffe000u, bh1 = __float_as_uint(b1) & 0xffffe000u;
-                    const uint32_t bl0 = __float_as_uint(b0 - __uint_as_float(bh0));
-                    const uint32_t bl1 = __float_as_uint(b1 - __uint_as_float(bh1));
-                    mma_tf32_1688(s[nt], al, bh0, bh1);
-                    mma_tf32_1688(s[nt], ah, bl0, bl1);
-                    mma_tf32_1688(s[nt], ah, bh0, bh1);
+                    const float4 fj = *reinterpret_cast<const float4*>(bj + nt * 4096);
+                    uint32_t bh[4], bl[4];
+                    split(fj.x, bh[0], bl[0]), split(fj.y, bh[1], bl[1]), split(fj.z, bh[2], bl[2]), split(fj.w, bh[3], bl[3]);
+#pragma unroll
+                    for (int k2 = 0; k2 < 2; ++k2) {
+                        mma_tf32_1688(s[nt], al[k2], bh[2 * k2], bh[2 * k2 + 1]);
+                        mma_tf32_1688(s[nt], ah[k2], bl[2 * k2], bl[2 * k2 + 1]);
+                        mma_tf32_1688(s[nt], ah[k2], bh[2 * k2], bh[2 * k2 + 1]);
+                    }
                 }
             }
         }
 #pragma unroll
         for (int hrow = 0; hrow < 2; ++hrow) {
-            // 4th largest with multiplicity (torch.topk): walk down the distinct values, counting copies
-            // (all lanes run the four rounds: the quads of a warp finish at different rounds and shuffle together)
-            float cur = INFINITY, thr = -INFINITY;
-            int rem = 4;
-            bool done = false;
-#pragma unroll 1
-            for (int it = 0; it < 4; ++it) {
-                float m = -INFINITY;
+            // 4th largest with multiplicity (torch.topk) by sorting networks, as in similarity_topk_impl
+            float best[4];
 #pragma unroll
-                for (int nt = 0; nt < 32; ++nt)
+            for (int g4 = 0; g4 < 16; ++g4) {
+                float c[4];
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const float v = s[nt][hrow * 2 + i];
-                        if (nt * 8 + t4 * 2 + i < T && v < cur) m = fmaxf(m, v);
-                    }
-                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-                int cnt = 0;
+                for (int q = 0; q < 4; ++q) {
+                    const int nt = 2 * g4 + (q >> 1), i = q & 1;
+                    c[q] = (nt * 8 + t4 * 2 + i < T) ? s[nt][hrow * 2 + i] : -INFINITY;
+                }
+                sort4_desc(c);
+                if (g4 == 0) {
 #pragma unroll
-                for (int nt = 0; nt < 32; ++nt)
-#pragma unroll
-                    for (int i = 0; i < 2; ++i)
-                        cnt += (nt * 8 + t4 * 2 + i < T && s[nt][hrow * 2 + i] == m) ? 1 : 0;
-                cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
-                cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
-                if (!done) {
-                    thr = m;
-                    if (cnt >= rem) done = true;
-                    rem -= cnt;
-                    cur = m;
+                    for (int i = 0; i < 4; ++i) best[i] = c[i];
+                } else {
+                    merge_top4(best, c);
                 }
             }
+            float o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = __shfl_xor_sync(0xffffffffu, best[i], 1);
+            merge_top4(best, o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = __shfl_xor_sync(0xffffffffu, best[i], 2);
+            const float thr = fminf(fminf(fmaxf(best[0], o[3]), fmaxf(best[1], o[2])), fminf(fmaxf(best[2], o[1]), fmaxf(best[3], o[0])));
             const int row = mt * 16 + g8 + hrow * 8;
             int deg = 0;
 #pragma unroll
