@@ -242,9 +242,15 @@ def run_ours(args):
         kinds = [("attention", "spatial"), ("attention", "temporal"), ("graph", "spatial"), ("graph", "temporal"),
                  ("bone", "spatial"), ("bone", "temporal")]
         per_kind_ms = {n: 0.0 for n in names}
-        for l in range(26):
-            for i, n in enumerate(names):
-                per_kind_ms[n] += per_launch[1 + l * 7 + i]
+        # kasf_forward micro-batches large B: every pass contributes 1 (features) + 26 x 7 + 1 (head) marks
+        per_pass = 1 + 26 * 7 + 1
+        passes = n_marks // per_pass
+        feat_ms = sum(per_launch[ps * per_pass] for ps in range(passes))
+        head_ms = sum(per_launch[ps * per_pass + per_pass - 1] for ps in range(passes))
+        for ps in range(passes):
+            for l in range(26):
+                for i, n in enumerate(names):
+                    per_kind_ms[n] += per_launch[ps * per_pass + 1 + l * 7 + i]
         mod_ms = sum(per_kind_ms[n] for n in names[:6])
         mod_flops = 26 * sum(2.0 * module_macs_per_token(k, m, T) * tokens for k, m in kinds)
         achieved = mod_flops / (mod_ms / 1e3) / 1e12
@@ -260,7 +266,7 @@ def run_ours(args):
                 traffic, traffic_src = sum(per) / len(per), tj["capture"]
         # algorithmic HBM bytes per launch: 512 B read + 512 B written per token (+ 256 B of the bf16 limb tile in the
         # two bone modules): mean over the six instantiations
-        alg_bytes = tokens * (512 * 2 * 6 + 256 * 2) / 6
+        alg_bytes = tokens / passes * (512 * 2 * 6 + 256 * 2) / 6
         out = {
             "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -276,11 +282,11 @@ def run_ours(args):
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
                          "frac": achieved / pk["bf16"], "traffic": traffic, "traffic_unit": "bytes/launch (dram read+write, ncu)",
                          "traffic_source": traffic_src, "algorithmic_bytes_per_launch": alg_bytes,
-                         "algorithmic_flops_per_launch": mod_flops / 156, "peak_source": pk["src"],
-                         "kernel": "former_module_kernel<KIND,MODE> (6 instantiations, 156 launches/forward)",
+                         "algorithmic_flops_per_launch": mod_flops / (156 * passes), "peak_source": pk["src"],
+                         "kernel": f"former_module_kernel<KIND,MODE> (6 instantiations, {156 * passes} launches/forward)",
                          "share_of_step": mod_ms / step_ms,
                          "per_kind_ms_per_forward": {k: round(v, 4) for k, v in per_kind_ms.items()},
-                         "other_ms": {"features": round(per_launch[0], 4), "head": round(per_launch[-1], 4)},
+                         "other_ms": {"features": round(feat_ms, 4), "head": round(head_ms, 4)},
                          "whole_forward_frac": value / world * flops_per_clip(T) / 1e12 / pk["bf16"]},
         }
         if world == 1 and not args.no_cpu:

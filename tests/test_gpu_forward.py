@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from conftest import load_golden
-from kasportsformer_b200 import KASportsFormer, synthetic
+from kasportsformer_b200 import _capi, KASportsFormer, synthetic
 from oracle import kasf_oracle as O
 from oracle import metrics_oracle as MO
 
@@ -90,6 +90,20 @@ def test_forward_properties():
     assert torch.equal(x2, x)                       # input not mutated
     y[:, :, 0, :] = 0                               # output is a fresh writable tensor (…_sp.py:55)
     assert m(x[:0]).shape == (0, 27, 17, 3)         # empty batch
+
+
+def test_forward_micro_batched_large_B():
+    """B beyond the ~3 GiB workspace bound (2,284 clips at T=27) runs as several passes over the same workspace
+    (the 256-65,536 clip sweep of BASELINE.json configs[4]): bit-identical to evaluating the parts separately."""
+    cfg = dict(n_layers=1, n_frames=27, dim_feat=128, dim_rep=512, num_heads=8, mlp_ratio=4, num_joints=17,
+               neighbour_num=4)
+    m = _model(cfg, 4, "stress")
+    B = 2500
+    assert _capi.forward_marks(cfg, B) == 2 * (1 + 7 + 1)          # two passes
+    x = synthetic.make_clips(B, 27, 11, "det").to(DEV)
+    y = m(x)
+    assert torch.equal(y[:1000], m(x[:1000])) and torch.equal(y[2284:], m(x[2284:]))
+    assert torch.isfinite(y).all()
 
 
 def test_module_contract():
