@@ -979,6 +979,9 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                     PMARK(6);
                 }
                 // ---- aggregation  agg_i = sum_j A_ij / sqrt(d_i d_j) * z_j : this thread's 64 columns of its row
+                //      (measured slower: all four neighbour slots branch-free with zero weights -- twice the loads, 5.8k vs
+                //       4.4k cycles per tile; warp-per-row with conflict-free row loads -- the rows of a warp serialise
+                //       their adjacency -> degree -> row dependency chains, 7.5k / 18k)
                 float rs = 0.f;
                 uint4 agg8[8];                             // split path: A_hat z of this row (bf16) from scratch
                 if (POST) {
@@ -1396,78 +1399,113 @@ __global__ void __launch_bounds__(256, 1) long_attention_kernel(const ModParams 
     const int g8 = lane >> 2, t4 = lane & 3, mi = lane >> 3, r8 = lane & 7;
     const float scale = 0.25f * 1.4426950408889634f;
     const int mtiles = (T + 15) >> 4, nkb = (T + 63) >> 6;        // 16-query blocks, 64-key blocks
+    // Two query blocks per round (U = 2): their ldmatrix -> mma -> ex2 -> mma chains are independent, which is the
+    // only instruction-level parallelism a warp has here (one block at a time left both pipes mostly idle; keeping
+    // all scores of a block in registers for a single pass was slower still: the eight warps then run their
+    // mma-only and MUFU-only phases in lock-step).
+    constexpr int U = 2;
 #pragma unroll 1
-    for (int mt = 0; mt < mtiles; ++mt) {
-        uint32_t qa[4];
-        ldsm_x4(qb + la_off(mt * 16 + (mi & 1) * 8 + r8, 2 * h + (mi >> 1)), qa);
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-        auto scores = [&](int kblk, float (&s)[8][4]) {
+    for (int mt0 = 0; mt0 < mtiles; mt0 += U) {
+        uint32_t qa[U][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int mt = min(mt0 + u, mtiles - 1);             // (odd count: the last round repeats a block)
+            ldsm_x4(qb + la_off(mt * 16 + (mi & 1) * 8 + r8, 2 * h + (mi >> 1)), qa[u]);
+        }
+        float mx0[U], mx1[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) mx0[u] = -INFINITY, mx1[u] = -INFINITY;
+        auto scores = [&](int kblk, float (&s)[U][8][4]) {
 #pragma unroll
             for (int nt = 0; nt < 8; nt += 2) {
                 uint32_t kf[4];
                 ldsm_x4(kb + la_off(kblk * 64 + 8 * (nt + (mi >> 1)) + r8, 2 * h + (mi & 1)), kf);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) s[nt][i] = 0.f, s[nt + 1][i] = 0.f;
-                mma_bf16_16816(s[nt], qa, kf[0], kf[1]);
-                mma_bf16_16816(s[nt + 1], qa, kf[2], kf[3]);
+                for (int u = 0; u < U; ++u) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) s[u][nt][i] = 0.f, s[u][nt + 1][i] = 0.f;
+                    mma_bf16_16816(s[u][nt], qa[u], kf[0], kf[1]);
+                    mma_bf16_16816(s[u][nt + 1], qa[u], kf[2], kf[3]);
+                }
             }
+            if (kblk * 64 + 64 > T) {                             // only the last key block holds keys past the end
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt)
+                for (int u = 0; u < U; ++u)
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (kblk * 64 + nt * 8 + t4 * 2 + (i & 1) >= T) s[nt][i] = -INFINITY;
+                    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (kblk * 64 + nt * 8 + t4 * 2 + (i & 1) >= T) s[u][nt][i] = -INFINITY;
+            }
         };
 #pragma unroll 1
         for (int kblk = 0; kblk < nkb; ++kblk) {                 // pass 1: row maxima
-            float s[8][4];
+            float s[U][8][4];
             scores(kblk, s);
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
-                mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
-            }
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    mx0[u] = fmaxf(mx0[u], fmaxf(s[u][nt][0], s[u][nt][1]));
+                    mx1[u] = fmaxf(mx1[u], fmaxf(s[u][nt][2], s[u][nt][3]));
+                }
         }
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        const float nm0 = -mx0 * scale, nm1 = -mx1 * scale;
-        float l0 = 0.f, l1 = 0.f, o[2][4];
+        float nm0[U], nm1[U], l0[U], l1[U], o[U][2][4];
 #pragma unroll
-        for (int dn = 0; dn < 2; ++dn)
+        for (int u = 0; u < U; ++u) {
+            mx0[u] = fmaxf(mx0[u], __shfl_xor_sync(0xffffffffu, mx0[u], 1));
+            mx1[u] = fmaxf(mx1[u], __shfl_xor_sync(0xffffffffu, mx1[u], 1));
+            mx0[u] = fmaxf(mx0[u], __shfl_xor_sync(0xffffffffu, mx0[u], 2));
+            mx1[u] = fmaxf(mx1[u], __shfl_xor_sync(0xffffffffu, mx1[u], 2));
+            nm0[u] = -mx0[u] * scale, nm1[u] = -mx1[u] * scale;
+            l0[u] = 0.f, l1[u] = 0.f;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) o[dn][i] = 0.f;
+            for (int dn = 0; dn < 2; ++dn)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o[u][dn][i] = 0.f;
+        }
 #pragma unroll 1
         for (int kblk = 0; kblk < nkb; ++kblk) {                 // pass 2: probabilities, P V
-            float s[8][4];
+            float s[U][8][4];
             scores(kblk, s);
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                s[nt][0] = ex2_approx(fmaf(s[nt][0], scale, nm0)), s[nt][1] = ex2_approx(fmaf(s[nt][1], scale, nm0));
-                s[nt][2] = ex2_approx(fmaf(s[nt][2], scale, nm1)), s[nt][3] = ex2_approx(fmaf(s[nt][3], scale, nm1));
-                l0 += s[nt][0] + s[nt][1];
-                l1 += s[nt][2] + s[nt][3];
-            }
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    s[u][nt][0] = ex2_approx(fmaf(s[u][nt][0], scale, nm0[u])), s[u][nt][1] = ex2_approx(fmaf(s[u][nt][1], scale, nm0[u]));
+                    s[u][nt][2] = ex2_approx(fmaf(s[u][nt][2], scale, nm1[u])), s[u][nt][3] = ex2_approx(fmaf(s[u][nt][3], scale, nm1[u]));
+                    l0[u] += s[u][nt][0] + s[u][nt][1];
+                    l1[u] += s[u][nt][2] + s[u][nt][3];
+                }
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-                uint32_t pa[4], vf[4];
-                pa[0] = pack_bf16(s[2 * ks][0], s[2 * ks][1]), pa[1] = pack_bf16(s[2 * ks][2], s[2 * ks][3]);
-                pa[2] = pack_bf16(s[2 * ks + 1][0], s[2 * ks + 1][1]), pa[3] = pack_bf16(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+                uint32_t vf[4];
                 ldsm_x4_t(vb + la_off(kblk * 64 + 16 * ks + (mi & 1) * 8 + r8, 2 * h + (mi >> 1)), vf);
-                mma_bf16_16816(o[0], pa, vf[0], vf[1]);
-                mma_bf16_16816(o[1], pa, vf[2], vf[3]);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    uint32_t pa[4];
+                    pa[0] = pack_bf16(s[u][2 * ks][0], s[u][2 * ks][1]), pa[1] = pack_bf16(s[u][2 * ks][2], s[u][2 * ks][3]);
+                    pa[2] = pack_bf16(s[u][2 * ks + 1][0], s[u][2 * ks + 1][1]), pa[3] = pack_bf16(s[u][2 * ks + 1][2], s[u][2 * ks + 1][3]);
+                    mma_bf16_16816(o[u][0], pa, vf[0], vf[1]);
+                    mma_bf16_16816(o[u][1], pa, vf[2], vf[3]);
+                }
             }
         }
-        l0 += __shfl_xor_sync(0xffffffffu, l0, 1), l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-        l0 += __shfl_xor_sync(0xffffffffu, l0, 2), l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-        const float i0 = rcp_approx(l0), i1 = rcp_approx(l1);
         // the output of this (head, query block) replaces the Q block this warp alone reads
         __syncwarp();
 #pragma unroll
-        for (int dn = 0; dn < 2; ++dn) {
-            const int r0 = mt * 16 + g8, r1 = r0 + 8;
-            *reinterpret_cast<uint32_t*>(sm + la_off(r0, 2 * h + dn) + t4 * 4) = pack_bf16(o[dn][0] * i0, o[dn][1] * i0);
-            *reinterpret_cast<uint32_t*>(sm + la_off(r1, 2 * h + dn) + t4 * 4) = pack_bf16(o[dn][2] * i1, o[dn][3] * i1);
+        for (int u = 0; u < U; ++u) {
+            if (mt0 + u < mtiles) {
+                l0[u] += __shfl_xor_sync(0xffffffffu, l0[u], 1), l1[u] += __shfl_xor_sync(0xffffffffu, l1[u], 1);
+                l0[u] += __shfl_xor_sync(0xffffffffu, l0[u], 2), l1[u] += __shfl_xor_sync(0xffffffffu, l1[u], 2);
+                const float i0 = rcp_approx(l0[u]), i1 = rcp_approx(l1[u]);
+#pragma unroll
+                for (int dn = 0; dn < 2; ++dn) {
+                    const int r0 = (mt0 + u) * 16 + g8, r1 = r0 + 8;
+                    *reinterpret_cast<uint32_t*>(sm + la_off(r0, 2 * h + dn) + t4 * 4) = pack_bf16(o[u][dn][0] * i0, o[u][dn][1] * i0);
+                    *reinterpret_cast<uint32_t*>(sm + la_off(r1, 2 * h + dn) + t4 * 4) = pack_bf16(o[u][dn][2] * i1, o[u][dn][3] * i1);
+                }
+            }
         }
     }
     __syncthreads();
