@@ -227,25 +227,25 @@ __device__ __forceinline__ void ln_stats(uint8_t* sm, const EpiMap& e, const flo
     rstd = 1.0f / sqrtf(var + 1e-5f);
 }
 
-// z = (x - mean) * rstd * gamma + beta for this thread's 64 columns -> bf16 A operand tile (+ fp32 copy in AUX)
-template <bool Z_TO_AUX>
+// z = (x - mean) * rstd [* gamma + beta] for this thread's 64 columns -> bf16 A operand tile (+ fp32 copy in AUX).
+// AFFINE = false wherever the LayerNorm's affine is folded into the weights it feeds (kasf_pack.cu): LN1 / LN_limb of
+// the attention and bone modules, LN2 of every module; only the GCN's LN1 keeps it (z itself is used in fp32).
+template <bool Z_TO_AUX, bool AFFINE>
 __device__ __forceinline__ void ln_write(uint8_t* sm, uint32_t a_tile, const EpiMap& e, const float (&xv)[64], float mean,
                                          float rstd, const float* gamma, const float* beta, bool ok) {
     const float nm = -mean * rstd;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         const int col = e.half * 64 + c * 8;
-        const float4 g0 = *reinterpret_cast<const float4*>(gamma + col), g1 = *reinterpret_cast<const float4*>(gamma + col + 4);
-        const float4 b0 = *reinterpret_cast<const float4*>(beta + col), b1 = *reinterpret_cast<const float4*>(beta + col + 4);
         float z[8];
-        z[0] = fmaf(fmaf(xv[c * 8 + 0], rstd, nm), g0.x, b0.x);
-        z[1] = fmaf(fmaf(xv[c * 8 + 1], rstd, nm), g0.y, b0.y);
-        z[2] = fmaf(fmaf(xv[c * 8 + 2], rstd, nm), g0.z, b0.z);
-        z[3] = fmaf(fmaf(xv[c * 8 + 3], rstd, nm), g0.w, b0.w);
-        z[4] = fmaf(fmaf(xv[c * 8 + 4], rstd, nm), g1.x, b1.x);
-        z[5] = fmaf(fmaf(xv[c * 8 + 5], rstd, nm), g1.y, b1.y);
-        z[6] = fmaf(fmaf(xv[c * 8 + 6], rstd, nm), g1.z, b1.z);
-        z[7] = fmaf(fmaf(xv[c * 8 + 7], rstd, nm), g1.w, b1.w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z[i] = fmaf(xv[c * 8 + i], rstd, nm);
+        if (AFFINE) {
+            const float4 g0 = *reinterpret_cast<const float4*>(gamma + col), g1 = *reinterpret_cast<const float4*>(gamma + col + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(beta + col), b1 = *reinterpret_cast<const float4*>(beta + col + 4);
+            z[0] = fmaf(z[0], g0.x, b0.x), z[1] = fmaf(z[1], g0.y, b0.y), z[2] = fmaf(z[2], g0.z, b0.z), z[3] = fmaf(z[3], g0.w, b0.w);
+            z[4] = fmaf(z[4], g1.x, b1.x), z[5] = fmaf(z[5], g1.y, b1.y), z[6] = fmaf(z[6], g1.z, b1.z), z[7] = fmaf(z[7], g1.w, b1.w);
+        }
         if (!ok) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) z[i] = 0.f;
@@ -869,7 +869,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 csync();                                   // every limb row is in registers: the staging buffer
                 gather_rows<MODE>(p, sm, tile, p.in, &bars[B_ROWS], warp, lane);   // receives the residual rows
                 ln_stats(sm, e, xv, mean, rstd);
-                ln_write<false>(sm, SM_A1, e, xv, mean, rstd, vec + V_NLW, vec + V_NLB, row_ok);
+                ln_write<false, false>(sm, SM_A1, e, xv, mean, rstd, nullptr, nullptr, row_ok);
                 warp_arrive(&bars[B_AREADY], lane);
                 PMARK(0);
             }
@@ -899,7 +899,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                     tc_fence_after();
                 }
                 if (KIND == KASF_KIND_GRAPH) csync();      // z (fp32) overwrites the staging rows of other threads
-                ln_write<KIND == KASF_KIND_GRAPH>(sm, SM_A1, e, xv, mean, rstd, vec + V_N1W, vec + V_N1B, row_ok);
+                ln_write<KIND == KASF_KIND_GRAPH, KIND == KASF_KIND_GRAPH>(sm, SM_A1, e, xv, mean, rstd, vec + V_N1W, vec + V_N1B, row_ok);
             }
             tmem_st_wait();
             warp_arrive(&bars[B_AREADY], lane);
@@ -1101,7 +1101,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
             }
             PMARK(9);
             ln_stats(sm, e, xv, mean, rstd);
-            ln_write<false>(sm, SM_A0, e, xv, mean, rstd, vec + V_N2W, vec + V_N2B, row_ok);
+            ln_write<false, false>(sm, SM_A0, e, xv, mean, rstd, nullptr, nullptr, row_ok);
             tmem_st_wait();
             warp_arrive(&bars[B_AREADY], lane);
             PMARK(10);
@@ -1301,7 +1301,7 @@ __global__ void __launch_bounds__(256, 1) long_pre_kernel(const ModParams p) {
     if (KIND == KASF_KIND_BONE) {
         load_row(p.xl);
         ln_stats(sm, e, xv, mean, rstd);
-        ln_write<false>(sm, SM_A0, e, xv, mean, rstd, vec + V_NLW, vec + V_NLB, row_ok);
+        ln_write<false, false>(sm, SM_A0, e, xv, mean, rstd, nullptr, nullptr, row_ok);
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
@@ -1317,7 +1317,7 @@ __global__ void __launch_bounds__(256, 1) long_pre_kernel(const ModParams p) {
     }
     load_row(p.in);
     ln_stats(sm, e, xv, mean, rstd);
-    ln_write<false>(sm, SM_A0, e, xv, mean, rstd, vec + V_N1W, vec + V_N1B, row_ok);
+    ln_write<false, false>(sm, SM_A0, e, xv, mean, rstd, nullptr, nullptr, row_ok);
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {

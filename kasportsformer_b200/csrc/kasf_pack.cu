@@ -43,8 +43,10 @@ __global__ void pack_chunks_kernel(const float* __restrict__ img, uint8_t* __res
     // output-projection bias (pack_vectors_kernel)
     // likewise LN1's gamma is folded into the Q|K|V (attention) / Q (bone) weight columns: their operand is the
     // normalised stream row, which a producer kernel can hand over ready-made (see xhat tiles in kasf_module.cu)
+    // ... and LN2's gamma into the fc1 weight columns of every module (beta: fc1 bias, pack_vectors_kernel)
     const float* kscale = (pm.kind == 2 && (c == 1 || c == 2)) ? img + pm.img.nlw
-                          : ((pm.kind == 0 && c < 3) || (pm.kind == 2 && c == 0)) ? img + pm.img.n1w : nullptr;
+                          : ((pm.kind == 0 && c < 3) || (pm.kind == 2 && c == 0)) ? img + pm.img.n1w
+                          : (c >= 4 && c < 8) ? img + pm.img.n2w : nullptr;
     for (int i = threadIdx.x; i < 128 * 64; i += blockDim.x) {   // pairs of k
         const int n = i >> 6, k = (i & 63) * 2;
         float v0 = 0.f, v1 = 0.f;
@@ -148,8 +150,12 @@ __global__ void pack_vectors_kernel(const float* __restrict__ img, uint8_t* __re
         }
     }
     for (int i = threadIdx.x; i < HID; i += blockDim.x) {
-        v[V_B1 + i] = img[m.fc1b + i];
-        reinterpret_cast<__half*>(v + V_B1H)[i] = __float2half_rn(img[m.fc1b + i]);
+        // fc1 bias + W1 beta_2: LN2's affine is folded into fc1 (the kernels write the plain normalised row)
+        const float* w1 = img + m.fc1w + (size_t)i * D;
+        float acc = img[m.fc1b + i];
+        for (int k = 0; k < D; ++k) acc = fmaf(w1[k], img[m.n2b + k], acc);
+        v[V_B1 + i] = acc;
+        reinterpret_cast<__half*>(v + V_B1H)[i] = __float2half_rn(acc);
     }
     if (pm.kind == 1)
         for (int i = threadIdx.x; i < pm.nodes; i += blockDim.x) {

@@ -235,9 +235,18 @@ def gcn_mixer(state: State, pre: str, z: Tensor, mode: str, neighbour_num: int,
     return out.reshape(B, T, J, C)
 
 
-def mlp(state: State, pre: str, z: Tensor) -> Tensor:
-    """reference model/modules/mlp.py:24-30."""
-    h = gelu_erf(linear(z, state[pre + "fc1.weight"], state[pre + "fc1.bias"]))
+def mlp(state: State, pre: str, z: Tensor, norm: Optional[tuple] = None) -> Tensor:
+    """reference model/modules/mlp.py:24-30.
+
+    norm = (x, gamma, beta) lets the bf16-emulating mode follow the kernels, which fold LN2's affine into fc1
+    (operand = the normalised row rounded to bf16, weight = bf16(W1 diag(gamma)), bias = b1 + W1 beta in fp32)."""
+    if EMULATE_BF16 and norm is not None:
+        x, gamma, beta = norm
+        w1 = state[pre + "fc1.weight"]
+        xhat = F.layer_norm(x, (x.shape[-1],), None, None, 1e-5)
+        h = gelu_erf(F.linear(_q(xhat), _q(w1 * gamma[None, :]), state[pre + "fc1.bias"] + w1 @ beta))
+    else:
+        h = gelu_erf(linear(z, state[pre + "fc1.weight"], state[pre + "fc1.bias"]))
     if EMULATE_BF16:
         # the kernels keep the hidden activation and the fc2 weights in fp16 (fc2 is an f16 x f16 -> fp32 MMA)
         w2 = state[pre + "fc2.weight"]
@@ -267,7 +276,8 @@ def former_module(state: State, pre: str, v: Tensor, xl: Optional[Tensor], kind:
     v = v + state[pre + "layer_scale_1"] * m
     if hook:
         hook(pre + "mid", v)
-    h = mlp(state, pre + "mlp.", layer_norm(v, state[pre + "norm2.weight"], state[pre + "norm2.bias"]))
+    h = mlp(state, pre + "mlp.", layer_norm(v, state[pre + "norm2.weight"], state[pre + "norm2.bias"]),
+            (v, state[pre + "norm2.weight"], state[pre + "norm2.bias"]))
     if hook:
         hook(pre + "mlp", h)
     v = v + state[pre + "layer_scale_2"] * h
