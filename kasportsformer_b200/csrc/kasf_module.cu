@@ -629,21 +629,24 @@ __device__ __forceinline__ int tile_rows(const ModParams& p, int tile) {
 // completion of its copies to `bar`.  Issued right after fc2 completes: the rows land behind the output epilogue.
 template <int MODE>
 __device__ __forceinline__ void gather_rows(const ModParams& p, uint8_t* sm, int tile, const float* src, uint64_t* bar,
-                                            int warp, int lane) {
+                                            int warp, int lane, int part) {
+    // part 0: rows 0..63 (they land in B1, free as soon as fc2 of hidden chunk 2 has read it), part 1: rows 64..127
+    // (B2, free after the last fc2 chunk).  Every lane attaches its copies to `bar` once per part.
     const int n = tile_rows<MODE>(p, tile);
+    const int lo = part * 64, hi = min(n, lo + 64);
     if (MODE == KASF_MODE_SPATIAL) {
         const float* g = src + (long long)tile * 119 * D + lane * 4;
 #pragma unroll 4
-        for (int r = warp; r < n; r += CW) cp_async16(sm + SM_STAGE + f32_off(r, lane), g + (size_t)r * D, 16u);
+        for (int r = lo + warp; r < hi; r += CW) cp_async16(sm + SM_STAGE + f32_off(r, lane), g + (size_t)r * D, 16u);
     } else {
-        // lane l (< 16) knows the token of row warp + 8 l; broadcast row by row
-        const int myrow = warp + CW * (lane & 15);
-        const int mytok = myrow < n ? (int)row_token<MODE>(p, tile, myrow) : 0;
-#pragma unroll 4
-        for (int k = 0; k < 16; ++k) {
+        // lane l (< 8) knows the token of row lo + warp + 8 l; broadcast row by row
+        const int myrow = lo + warp + CW * (lane & 7);
+        const int mytok = myrow < hi ? (int)row_token<MODE>(p, tile, myrow) : 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
             const int tok = __shfl_sync(0xffffffffu, mytok, k);
-            const int r = warp + CW * k;
-            if (r < n) cp_async16(sm + SM_STAGE + f32_off(r, lane), src + (size_t)tok * D + lane * 4, 16u);
+            const int r = lo + warp + CW * k;
+            if (r < hi) cp_async16(sm + SM_STAGE + f32_off(r, lane), src + (size_t)tok * D + lane * 4, 16u);
         }
     }
     cp_async_mbar_arrive(bar);
@@ -694,7 +697,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
         if ((smem_u32(sm) & 1023u) != 0) __trap();
         for (int i = 0; i < B_COUNT; ++i) {
             const bool by_warps = i == B_AREADY || i == B_HSREADY0 || i == B_HSREADY1;
-            mbar_init(&bars[i], (by_warps || i == B_OUTDONE) ? CW : (i == B_ROWS ? CW * 32 : 1));
+            mbar_init(&bars[i], (by_warps || i == B_OUTDONE) ? CW : (i == B_ROWS ? CW * 32 * 2 : 1));   // ROWS: two half gathers
         }
         fence_mbar_init();
     }
@@ -824,7 +827,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                         if (c == 1 && limb_tiles) tc_commit(&bars[B_A0FREE]);   // last reader of the A tile
                     }
                     chunk(TM_OUT, hs_addr + buf * TILE_BYTES, c > 0, KASF_HALF_GELU != 0);   // fc2: fp16 x fp16
-                    if (c < 2) tc_commit(&bars[buf ? B_HSFREE1 : B_HSFREE0]);
+                    if (c < 3) tc_commit(&bars[buf ? B_HSFREE1 : B_HSFREE0]);   // (c == 2: B1 is free for the next tile's rows)
                     if (c == 3) tc_commit(&bars[B_OUT]);
                 }
             }
@@ -852,7 +855,8 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
         }                                                             \
     } while (0)
 
-        gather_rows<MODE>(p, sm, blockIdx.x, first_src, &bars[B_ROWS], warp, lane);
+        gather_rows<MODE>(p, sm, blockIdx.x, first_src, &bars[B_ROWS], warp, lane, 0);
+        gather_rows<MODE>(p, sm, blockIdx.x, first_src, &bars[B_ROWS], warp, lane, 1);
         if (limb_tiles && lane == 0) mbar_arrive(&bars[B_OUTDONE]);   // no previous tile: the accumulator columns are free
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
             const int nrows = tile_rows<MODE>(p, tile);
@@ -867,7 +871,8 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 rows.wait();
                 read_staged(sm, e, xv, row_ok);
                 csync();                                   // every limb row is in registers: the staging buffer
-                gather_rows<MODE>(p, sm, tile, p.in, &bars[B_ROWS], warp, lane);   // receives the residual rows
+                gather_rows<MODE>(p, sm, tile, p.in, &bars[B_ROWS], warp, lane, 0);   // receives the residual rows
+                gather_rows<MODE>(p, sm, tile, p.in, &bars[B_ROWS], warp, lane, 1);
                 ln_stats(sm, e, xv, mean, rstd);
                 ln_write<false, false>(sm, SM_A1, e, xv, mean, rstd, nullptr, nullptr, row_ok);
                 warp_arrive(&bars[B_AREADY], lane);
@@ -1185,12 +1190,17 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 warp_arrive(&bars[buf ? B_HSREADY1 : B_HSREADY0], lane);
                 PMARK(11);
             }
+            // ---- B1 (hidden tile 0) was last read by fc2 of chunk 2: the first 64 rows of the next tile can be
+            //      requested a whole GELU epilogue + fc2 chunk earlier than the rest
+            hsfree0.wait();
+            if (tile + (int)gridDim.x < p.ntiles)
+                gather_rows<MODE>(p, sm, tile + (int)gridDim.x, first_src, &bars[B_ROWS], warp, lane, 0);
             outb.wait();
             tc_fence_after();
             PMARK(14);
-            // ---- B1|B2 are free: request the next tile's rows; they land while the output epilogue runs
+            // ---- B2 is free as well: request the other 64 rows; they land while the output epilogue runs
             if (tile + (int)gridDim.x < p.ntiles)
-                gather_rows<MODE>(p, sm, tile + (int)gridDim.x, first_src, &bars[B_ROWS], warp, lane);
+                gather_rows<MODE>(p, sm, tile + (int)gridDim.x, first_src, &bars[B_ROWS], warp, lane, 1);
             // ---- out = x1 + ls2 * (acc + b2): 256-bit stores of this thread's 64 columns, straight from registers
             //      (staging the rows in shared memory for coalesced 128-bit stores was measured slower: 4.4k vs 3.4k
             //       cycles per tile, the extra CTA barriers and the second pass over the data cost more than the LSU saves)
