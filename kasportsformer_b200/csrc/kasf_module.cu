@@ -160,16 +160,24 @@ __device__ __forceinline__ __half2 tanh_h2(__half2 w) {
 // "thread per row" access.
 __device__ __forceinline__ uint32_t f32_off(uint32_t r, uint32_t chunk) { return r * 512u + ((chunk ^ (r & 7u)) << 4); }
 
-struct WaitBar {
-    uint64_t* bar;
-    uint32_t phase;
-    __device__ __forceinline__ void wait() {
-#ifdef KASF_SUSPEND_WAITS
-        mbar_wait_suspend(bar, phase);
-#else
-        mbar_wait(bar, phase);
-#endif
-        phase ^= 1;
+// Waiter side of the mbarriers of a compute thread: one shared-memory base and ONE register of phase bits (bit i =
+// parity the thread expects next on barrier i), instead of a pointer and a phase per barrier
+struct Waiter {
+    uint32_t base;     // shared-space address of bars[0]
+    uint32_t phases;
+    __device__ __forceinline__ void wait(int idx) {
+        const uint32_t addr = base + idx * 8, parity = (phases >> idx) & 1u;
+        uint32_t ok;
+        do {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok)
+                : "r"(addr), "r"(parity)
+                : "memory");
+        } while (!ok);
+        phases ^= 1u << idx;
     }
 };
 
@@ -841,9 +849,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
         e.half = warp >> 2;
         e.warp = warp;
         e.tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        WaitBar mma{&bars[B_MMA], 0}, hfull0{&bars[B_HFULL0], 0}, hfull1{&bars[B_HFULL1], 0},
-            hsfree0{&bars[B_HSFREE0], 0}, hsfree1{&bars[B_HSFREE1], 0}, outb{&bars[B_OUT], 0}, rows{&bars[B_ROWS], 0},
-            mmak{&bars[B_MMAK], 0}, mmav{&bars[B_MMAV], 0};
+        Waiter wt{smem_u32(bars), 0u};
 
         long long pt0 = p.prof ? clock64() : 0;
 #define PMARK(k)                                                      \
@@ -868,7 +874,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
 
             if (KIND == KASF_KIND_BONE && !POST && !limb_tiles) {
                 // ---- K,V from the limb stream: LN_limb(XL) Wkv^T
-                rows.wait();
+                wt.wait(B_ROWS);
                 read_staged(sm, e, xv, row_ok);
                 csync();                                   // every limb row is in registers: the staging buffer
                 gather_rows<MODE>(p, sm, tile, p.in, &bars[B_ROWS], warp, lane, 0);   // receives the residual rows
@@ -879,7 +885,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 PMARK(0);
             }
             // ---- residual rows: staging -> registers -> tensor memory (resident); LN1 -> A operand
-            rows.wait();
+            wt.wait(B_ROWS);
             PMARK(13);
             read_staged(sm, e, xv, row_ok);
 #pragma unroll
@@ -900,7 +906,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
             } else {
                 ln_stats(sm, e, xv, mean, rstd);
                 if (KIND == KASF_KIND_BONE) {
-                    mma.wait();                            // K,V complete: the A tile may be overwritten
+                    wt.wait(B_MMA);                            // K,V complete: the A tile may be overwritten
                     tc_fence_after();
                 }
                 if (KIND == KASF_KIND_GRAPH) csync();      // z (fp32) overwrites the staging rows of other threads
@@ -911,7 +917,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
             PMARK(1);
 
             if (KIND != KASF_KIND_GRAPH && POST) {
-                mma.wait();                                // output projection
+                wt.wait(B_MMA);                                // output projection
                 tc_fence_after();
                 PMARK(5);
             } else if (KIND != KASF_KIND_GRAPH) {
@@ -952,10 +958,10 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 };
                 if (KIND == KASF_KIND_ATTENTION) {
                     // K complete => every warp has arrived on AREADY, i.e. has read its staged rows: AUX is free
-                    mmak.wait();
+                    wt.wait(B_MMAK);
                     tc_fence_after();
                     drain(1);
-                    mmav.wait();
+                    wt.wait(B_MMAV);
                     tc_fence_after();
                     drain(2);
                 } else {
@@ -963,7 +969,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                     drain(1);                              // K,V were complete before LN1(x) was written
                     drain(2);
                 }
-                mma.wait();                                // Q in tensor memory
+                wt.wait(B_MMA);                                // Q in tensor memory
                 tc_fence_after();
                 PMARK(2);
                 drain(0);
@@ -972,7 +978,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 attention_core<MODE, TC>(sm, warp, lane, gsize, nrows);
                 warp_arrive(&bars[B_AREADY], lane);
                 PMARK(4);
-                mma.wait();                                // output projection
+                wt.wait(B_MMA);                                // output projection
                 tc_fence_after();
                 PMARK(5);
             } else {
@@ -1041,7 +1047,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                     }
                 }
                 if (e.half == 0) *reinterpret_cast<float*>(sm + SM_ROWSUM + e.row * 4) = rs;
-                mma.wait();   // U z done: the A tile may be overwritten
+                wt.wait(B_MMA);   // U z done: the A tile may be overwritten
                 tc_fence_after();
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
@@ -1057,7 +1063,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 pair_sync(e.warp);                         // the row sum written by the partner thread (half 0)
                 warp_arrive(&bars[B_AREADY], lane);
                 PMARK(7);
-                mma.wait();                                // += (A_hat z) V^T
+                wt.wait(B_MMA);                                // += (A_hat z) V^T
                 tc_fence_after();
                 PMARK(8);
             }
@@ -1118,9 +1124,9 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 const int buf = c & 1;
-                if (buf) hfull1.wait(); else hfull0.wait();
+                wt.wait(buf ? B_HFULL1 : B_HFULL0);
                 tc_fence_after();
-                if (c >= 2) { if (buf) hsfree1.wait(); else hsfree0.wait(); }
+                if (c >= 2) { wt.wait(buf ? B_HSFREE1 : B_HSFREE0); }
                 PMARK(14);
                 uint32_t acc[2][32];
                 tmem_ld32(e.tbase + (buf ? TM_H1 : TM_H0) + e.half * 64, acc[0]);
@@ -1192,10 +1198,10 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
             }
             // ---- B1 (hidden tile 0) was last read by fc2 of chunk 2: the first 64 rows of the next tile can be
             //      requested a whole GELU epilogue + fc2 chunk earlier than the rest
-            hsfree0.wait();
+            wt.wait(B_HSFREE0);
             if (tile + (int)gridDim.x < p.ntiles)
                 gather_rows<MODE>(p, sm, tile + (int)gridDim.x, first_src, &bars[B_ROWS], warp, lane, 0);
-            outb.wait();
+            wt.wait(B_OUT);
             tc_fence_after();
             PMARK(14);
             // ---- B2 is free as well: request the other 64 rows; they land while the output epilogue runs
