@@ -507,13 +507,8 @@ __device__ __forceinline__ void similarity_topk_impl(uint8_t* sm, int warp, int 
             hi = __float_as_uint(v) & 0xffffe000u;
             lo = __float_as_uint(v - __uint_as_float(hi));
         };
-#ifdef KASF_DBG_SKIP_SIM
-#pragma unroll 1
-        for (int d = 0; d < 0; ++d) {
-#else
 #pragma unroll
         for (int d = 0; d < 8; ++d) {
-#endif
             // chunk 4 d + t4: 128-byte segment d >> 1, swizzled slot (t4 ^ x) [^ 4 for odd d]
             const int off = (d >> 1) * 128;
             const float4 fa = *reinterpret_cast<const float4*>(sm + ((zrow_a + off) ^ ((d & 1) << 6)));
