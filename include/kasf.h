@@ -146,7 +146,8 @@ int kasf_former_module_lt(const kasf_config* cfg, const void* packed_dev, int la
                           const float* in_dev, const float* XL_dev, const void* limb_tiles_dev,
                           float* out_dev, int B, void* scratch_dev, size_t scratch_bytes, void* stream);
 
-/* Profiling hook: same launch, additionally accumulating (atomicAdd by thread 0 of every CTA) the SM cycles
+/* Profiling hook (own kernel instantiations, n_frames <= 32 and fused path only; otherwise the counters stay zero):
+ * same launch, additionally accumulating (atomicAdd by thread 0 of every CTA) the SM cycles
  * spent in each phase of the kernel into phase_cycles_dev[24] (caller zeroes it): 0 limb K/V, 1 load+LN1,
  * 2 QKV MMA wait, 3 Q/K/V drain, 4 attention core, 5 projection MMA wait, 6 similarity/top-k, 7 aggregation,
  * 8 V MMA wait, 9 mixer epilogue, 10 LN2, 11 MLP epilogue compute, 12 output epilogue, 13 wait for the gathered

@@ -686,7 +686,9 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
 // MODE == KASF_MODE_LONG is the tail of the split path for sequences longer than a tile (T > 128): the mixer
 // core ran in its own kernels (kasf_long section below) and left the attention output / A_hat z in scratch;
 // this kernel then does projection -> residual -> LN2 -> MLP -> residual on plain 128-row tiles.
-template <int KIND, int MODE, int TC>
+// PROF: the per-phase cycle counters of kasf_former_module_profiled are compiled in (own instantiations, so that the
+// production kernels carry neither the clock registers nor the sixteen checks per tile)
+template <int KIND, int MODE, int TC, bool PROF = false>
 __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const ModParams p) {
     constexpr bool POST = MODE == KASF_MODE_LONG;
     extern __shared__ __align__(1024) uint8_t sm[];
@@ -846,10 +848,10 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
         e.tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         Waiter wt{smem_u32(bars), 0u};
 
-        long long pt0 = p.prof ? clock64() : 0;
+        long long pt0 = PROF ? clock64() : 0;
 #define PMARK(k)                                                      \
     do {                                                              \
-        if (p.prof && tid == 0) {                                     \
+        if (PROF && tid == 0) {                                       \
             const long long pt1 = clock64();                          \
             atomicAdd(p.prof + (k), (unsigned long long)(pt1 - pt0)); \
             pt0 = pt1;                                                \
@@ -1244,8 +1246,15 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
 
 template <int KIND, int MODE, int TC>
 static int launch_one(const ModParams& p, cudaStream_t st) {
-    cudaFuncSetAttribute(former_module_kernel<KIND, MODE, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
     const int grid = p.ntiles < 148 ? p.ntiles : 148;
+    if constexpr (TC == 0 && MODE != KASF_MODE_LONG) {     // profiling hook: short sequences only
+        if (p.prof) {
+            cudaFuncSetAttribute(former_module_kernel<KIND, MODE, TC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+            former_module_kernel<KIND, MODE, TC, true><<<grid, MOD_THREADS, SM_TOTAL, st>>>(p);
+            return cuda_status();
+        }
+    }
+    cudaFuncSetAttribute(former_module_kernel<KIND, MODE, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
     former_module_kernel<KIND, MODE, TC><<<grid, MOD_THREADS, SM_TOTAL, st>>>(p);
     return cuda_status();
 }
