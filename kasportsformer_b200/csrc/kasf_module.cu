@@ -326,7 +326,9 @@ __device__ __forceinline__ void attention_core_impl(uint8_t* sm, int warp, int l
             const int gh = GS ? item / mtiles : (int)(((uint32_t)item * inv_mtiles) >> 16);
             mt[u] = item - gh * mtiles, h[u] = gh & (HEADS - 1);
             gr0[u] = (gh >> 3) * gsize;
-            const int row = min(gr0[u] + mt[u] * 16 + (mi & 1) * 8 + r8, 127);
+            // (query rows past the end of the group repeat its last row: their results are dropped, and no item ever
+            //  reads the Q block another item may be overwriting with its output)
+            const int row = min(gr0[u] + mt[u] * 16 + (mi & 1) * 8 + r8, gr0[u] + gsize - 1);
             ldsm_x4(q_base + tile_off_bf16(row, h[u] * DH + (mi >> 1) * 8), qa[u]);
         }
 #pragma unroll
