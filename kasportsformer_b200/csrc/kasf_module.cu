@@ -438,10 +438,18 @@ __device__ __forceinline__ void attention_core_impl(uint8_t* sm, int warp, int l
 
 // TC = sequence-length class of the instantiation: 0: group size <= 32, 1: <= 64, 2: <= 128 (key tiles held in
 // registers).  One class per kernel keeps the cold variants out of the register allocation.
+// work items interleaved per warp (measured, profiles/r01z_attention_interleave.txt): two for short temporal groups,
+// four for the 17-joint spatial groups
+#ifndef KASF_ATT_U_T0
+#define KASF_ATT_U_T0 2
+#endif
+#ifndef KASF_ATT_U_S
+#define KASF_ATT_U_S 4
+#endif
 template <int MODE, int TC>
 __device__ __forceinline__ void attention_core(uint8_t* sm, int warp, int lane, int gsize, int nrows) {
-    if (MODE == KASF_MODE_SPATIAL) attention_core_impl<4, 4, J>(sm, warp, lane, gsize, nrows);
-    else if (TC == 0) attention_core_impl<4, 4, 0>(sm, warp, lane, gsize, nrows);
+    if (MODE == KASF_MODE_SPATIAL) attention_core_impl<4, KASF_ATT_U_S, J>(sm, warp, lane, gsize, nrows);
+    else if (TC == 0) attention_core_impl<4, KASF_ATT_U_T0, 0>(sm, warp, lane, gsize, nrows);
     else if (TC == 1) attention_core_impl<8, 2, 0>(sm, warp, lane, gsize, nrows);
     else attention_core_impl<16, 1, 0>(sm, warp, lane, gsize, nrows);
 }
