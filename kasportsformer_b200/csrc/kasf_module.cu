@@ -171,10 +171,14 @@ struct Waiter {
         do {
             asm volatile(
                 "{\n\t.reg .pred p;\n\t"
+#ifdef KASF_SUSPEND_WAITS
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+#else
                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#endif
                 "selp.u32 %0, 1, 0, p;\n\t}"
                 : "=r"(ok)
-                : "r"(addr), "r"(parity)
+                : "r"(addr), "r"(parity), "r"(0x989680u)
                 : "memory");
         } while (!ok);
         phases ^= 1u << idx;
@@ -487,7 +491,10 @@ __device__ __forceinline__ void similarity_topk_impl(uint8_t* sm, int warp, int 
         const int ra = min(m0 + g8, 127), rb = min(m0 + g8 + 8, 127);
         // hi*hi and the two cross terms accumulate in separate registers (short sequences): two independent MMA
         // dependency chains per key tile instead of one three times as long
-        constexpr bool SPLIT_ACC = MAXNT <= 8;
+#ifndef KASF_SIM_SPLIT_ACC
+#define KASF_SIM_SPLIT_ACC 1
+#endif
+        constexpr bool SPLIT_ACC = KASF_SIM_SPLIT_ACC && MAXNT <= 8;
         float s[MAXNT][4], sx[SPLIT_ACC ? MAXNT : 1][4];
 #pragma unroll
         for (int nt = 0; nt < MAXNT; ++nt)
