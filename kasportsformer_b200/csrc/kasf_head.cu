@@ -126,12 +126,21 @@ head_kernel(const float* __restrict__ gw, const float* __restrict__ X, float* __
         float acc0[HT], acc1[HT];
 #pragma unroll
         for (int r = 0; r < HT; ++r) acc0[r] = br0, acc1[r] = br1;
+        // weights of the next four k are requested before the current four are consumed (L2 latency off the FMA chain)
+        float w0[4], w1[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            w0[q] = Wt[q * REP + tid];
+            w1[q] = Wt[q * REP + tid + 256];
+        }
+#pragma unroll 1
         for (int k = 0; k < D; k += 4) {
-            float w0[4], w1[4];
+            float n0[4], n1[4];
+            const int kn = k + 4 < D ? k + 4 : k;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                w0[q] = Wt[(k + q) * REP + tid];
-                w1[q] = Wt[(k + q) * REP + tid + 256];
+                n0[q] = Wt[(kn + q) * REP + tid];
+                n1[q] = Wt[(kn + q) * REP + tid + 256];
             }
 #pragma unroll
             for (int r = 0; r < HT; ++r) {
@@ -145,6 +154,8 @@ head_kernel(const float* __restrict__ gw, const float* __restrict__ X, float* __
                 acc0[r] = fmaf(z.w, w0[3], acc0[r]);
                 acc1[r] = fmaf(z.w, w1[3], acc1[r]);
             }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) w0[q] = n0[q], w1[q] = n1[q];
         }
 #pragma unroll
         for (int r = 0; r < HT; ++r) {
