@@ -1,5 +1,7 @@
 // kasf_api.cu -- extern "C" entry points of libkasf.so (declared in include/kasf.h) and the
 // orchestration of the forward pass (reference model/KASportsFormer.py:320-347).
+#include <cstdlib>
+
 #include "kasf_internal.h"
 
 using namespace kasf;
@@ -223,6 +225,20 @@ static int forward_impl(const kasf_config* cfg, const void* packed_dev, const fl
     const int T = cfg->n_frames;
     const int chunk = clip_chunk(cfg, B);
     int ev = 0;
+    // side streams for the graph / bone branches (see the layer loop); created per call, the library keeps no state
+    bool side = false;
+    cudaStream_t side_s[2] = {nullptr, nullptr};
+    cudaEvent_t side_e[3] = {nullptr, nullptr, nullptr};
+    {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        const char* env = getenv("KASF_BRANCH_STREAMS");
+        const bool want = !events && T <= 128 && !(env && env[0] == '0');
+        if (want && cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
+            side = cudaStreamCreateWithFlags(&side_s[0], cudaStreamNonBlocking) == cudaSuccess &&
+                   cudaStreamCreateWithFlags(&side_s[1], cudaStreamNonBlocking) == cudaSuccess;
+            for (int i = 0; i < 3 && side; ++i) side = cudaEventCreateWithFlags(&side_e[i], cudaEventDisableTiming) == cudaSuccess;
+        }
+    }
 #define KASF_MARK() do { if (events) cudaEventRecord((cudaEvent_t)events[ev++], st); } while (0)
     KASF_MARK();
     for (int b0 = 0; b0 < B; b0 += chunk) {
@@ -237,35 +253,55 @@ static int forward_impl(const kasf_config* cfg, const void* packed_dev, const fl
         uint8_t* lt_t = lt_s + limb_tiles_bytes(chunk, T, KASF_MODE_SPATIAL);
         if (limb_tiles_bytes(chunk, T, KASF_MODE_TEMPORAL) == 0) lt_t = nullptr;
         const float* x = x_dev + (size_t)b0 * T * J * 3;
-        if ((rc = launch_features(blob, x, nullptr, nullptr, s.X, s.XB, s.XL, (long long)nb * T, st))) return rc;
-        if ((rc = launch_limb_tiles(s.XL, lt_s, nb, T, KASF_MODE_SPATIAL, st))) return rc;
-        if ((rc = launch_limb_tiles(s.XL, lt_t, nb, T, KASF_MODE_TEMPORAL, st))) return rc;
+        if ((rc = launch_features(blob, x, nullptr, nullptr, s.X, s.XB, s.XL, (long long)nb * T, st))) break;
+        if ((rc = launch_limb_tiles(s.XL, lt_s, nb, T, KASF_MODE_SPATIAL, st))) break;
+        if ((rc = launch_limb_tiles(s.XL, lt_t, nb, T, KASF_MODE_TEMPORAL, st))) break;
         KASF_MARK();
         for (int l = 0; l < cfg->n_layers; ++l) {
-            // three branches, each spatial module then temporal module (KASportsFormer.py:268-275)
+            // three branches, each spatial module then temporal module (KASportsFormer.py:268-275).  The branches are
+            // independent until the fusion, so (outside the timed / graph-captured / split-path cases) the graph and
+            // bone branches run on two side streams: the last, partial wave of one persistent kernel (26.7 tiles per SM
+            // at B = 1024) is filled by the first CTAs of another branch's kernel instead of idling.
             const float* bone_src = l == 0 ? s.XB : s.X;
-            if ((rc = launch_former_module(blob, l, KASF_KIND_ATTENTION, KASF_MODE_SPATIAL, s.X, nullptr, s.A, nb, T, st))) return rc;
+            cudaStream_t sg = side ? side_s[0] : st, sb = side ? side_s[1] : st;
+            if (side) {
+                cudaEventRecord(side_e[0], st);              // X of this layer is final
+                cudaStreamWaitEvent(sg, side_e[0], 0);
+                cudaStreamWaitEvent(sb, side_e[0], 0);
+            }
+            if ((rc = launch_former_module(blob, l, KASF_KIND_ATTENTION, KASF_MODE_SPATIAL, s.X, nullptr, s.A, nb, T, st))) break;
             KASF_MARK();
-            if ((rc = launch_former_module(blob, l, KASF_KIND_ATTENTION, KASF_MODE_TEMPORAL, s.A, nullptr, s.A, nb, T, st, nullptr, scr, scr_bytes))) return rc;
+            if ((rc = launch_former_module(blob, l, KASF_KIND_ATTENTION, KASF_MODE_TEMPORAL, s.A, nullptr, s.A, nb, T, st, nullptr, scr, scr_bytes))) break;
             KASF_MARK();
-            if ((rc = launch_former_module(blob, l, KASF_KIND_GRAPH, KASF_MODE_SPATIAL, s.X, nullptr, s.G, nb, T, st))) return rc;
+            if ((rc = launch_former_module(blob, l, KASF_KIND_GRAPH, KASF_MODE_SPATIAL, s.X, nullptr, s.G, nb, T, sg))) break;
             KASF_MARK();
-            if ((rc = launch_former_module(blob, l, KASF_KIND_GRAPH, KASF_MODE_TEMPORAL, s.G, nullptr, s.G, nb, T, st, nullptr, scr, scr_bytes))) return rc;
+            if ((rc = launch_former_module(blob, l, KASF_KIND_GRAPH, KASF_MODE_TEMPORAL, s.G, nullptr, s.G, nb, T, sg, nullptr, scr, scr_bytes))) break;
             KASF_MARK();
-            if ((rc = launch_former_module(blob, l, KASF_KIND_BONE, KASF_MODE_SPATIAL, bone_src, s.XL, s.Bn, nb, T, st, nullptr, nullptr, 0, lt_s))) return rc;
+            if ((rc = launch_former_module(blob, l, KASF_KIND_BONE, KASF_MODE_SPATIAL, bone_src, s.XL, s.Bn, nb, T, sb, nullptr, nullptr, 0, lt_s))) break;
             KASF_MARK();
-            if ((rc = launch_former_module(blob, l, KASF_KIND_BONE, KASF_MODE_TEMPORAL, s.Bn, s.XL, s.Bn, nb, T, st, nullptr, scr, scr_bytes, lt_t))) return rc;
+            if ((rc = launch_former_module(blob, l, KASF_KIND_BONE, KASF_MODE_TEMPORAL, s.Bn, s.XL, s.Bn, nb, T, sb, nullptr, scr, scr_bytes, lt_t))) break;
             KASF_MARK();
-            if ((rc = launch_fusion(blob, l, s.A, s.G, s.Bn, s.X, tokens, st))) return rc;
+            if (side) {
+                cudaEventRecord(side_e[1], sg);
+                cudaEventRecord(side_e[2], sb);
+                cudaStreamWaitEvent(st, side_e[1], 0);
+                cudaStreamWaitEvent(st, side_e[2], 0);
+            }
+            if ((rc = launch_fusion(blob, l, s.A, s.G, s.Bn, s.X, tokens, st))) break;
             KASF_MARK();
         }
+        if (rc) break;
         float* y = y_dev ? y_dev + (size_t)b0 * T * J * 3 : nullptr;
         float* rep = rep_dev ? rep_dev + (size_t)b0 * T * J * REP : nullptr;
-        if ((rc = launch_head(blob, s.X, y, rep, tokens, st))) return rc;
+        if ((rc = launch_head(blob, s.X, y, rep, tokens, st))) break;
         KASF_MARK();
     }
 #undef KASF_MARK
-    return KASF_OK;
+    for (int i = 0; i < 3; ++i)
+        if (side_e[i]) cudaEventDestroy(side_e[i]);
+    for (int i = 0; i < 2; ++i)
+        if (side_s[i]) cudaStreamDestroy(side_s[i]);   // (all their work is ordered before the caller's stream by the joins)
+    return rc;
 }
 
 int kasf_forward(const kasf_config* cfg, const void* packed_dev, const float* x_dev, float* y_dev, float* rep_dev,
