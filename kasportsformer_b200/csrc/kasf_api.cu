@@ -226,14 +226,15 @@ static int forward_impl(const kasf_config* cfg, const void* packed_dev, const fl
     const int chunk = clip_chunk(cfg, B);
     int ev = 0;
     // side streams for the graph / bone branches (see the layer loop); created per call, the library keeps no state
-    bool side = false;
+    bool side = false, capturing = false;
     cudaStream_t side_s[2] = {nullptr, nullptr};
     cudaEvent_t side_e[3] = {nullptr, nullptr, nullptr};
     {
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         const char* env = getenv("KASF_BRANCH_STREAMS");
         const bool want = !events && T <= 128 && !(env && env[0] == '0');
-        if (want && cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
+        if (want && cudaStreamIsCapturing(st, &cap) == cudaSuccess) {
+            capturing = cap != cudaStreamCaptureStatusNone;
             side = cudaStreamCreateWithFlags(&side_s[0], cudaStreamNonBlocking) == cudaSuccess &&
                    cudaStreamCreateWithFlags(&side_s[1], cudaStreamNonBlocking) == cudaSuccess;
             for (int i = 0; i < 3 && side; ++i) side = cudaEventCreateWithFlags(&side_e[i], cudaEventDisableTiming) == cudaSuccess;
@@ -259,7 +260,7 @@ static int forward_impl(const kasf_config* cfg, const void* packed_dev, const fl
         KASF_MARK();
         for (int l = 0; l < cfg->n_layers; ++l) {
             // three branches, each spatial module then temporal module (KASportsFormer.py:268-275).  The branches are
-            // independent until the fusion, so (outside the timed / graph-captured / split-path cases) the graph and
+            // independent until the fusion, so (outside the timed and split-path cases) the graph and
             // bone branches run on two side streams: the last, partial wave of one persistent kernel (26.7 tiles per SM
             // at B = 1024) is filled by the first CTAs of another branch's kernel instead of idling.
             const float* bone_src = l == 0 ? s.XB : s.X;
@@ -297,10 +298,15 @@ static int forward_impl(const kasf_config* cfg, const void* packed_dev, const fl
         KASF_MARK();
     }
 #undef KASF_MARK
-    for (int i = 0; i < 3; ++i)
-        if (side_e[i]) cudaEventDestroy(side_e[i]);
-    for (int i = 0; i < 2; ++i)
-        if (side_s[i]) cudaStreamDestroy(side_s[i]);   // (all their work is ordered before the caller's stream by the joins)
+    // (all side-stream work is ordered before the caller's stream by the joins.  Under stream capture the fork / join
+    //  becomes part of the captured graph and the two streams and three events are left alive with it: a few hundred
+    //  bytes per captured graph, never per replay)
+    if (!capturing) {
+        for (int i = 0; i < 3; ++i)
+            if (side_e[i]) cudaEventDestroy(side_e[i]);
+        for (int i = 0; i < 2; ++i)
+            if (side_s[i]) cudaStreamDestroy(side_s[i]);
+    }
     return rc;
 }
 
