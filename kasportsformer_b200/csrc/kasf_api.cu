@@ -103,7 +103,7 @@ size_t kasf_workspace_bytes(const kasf_config* cfg, int B) {
     if (config_ok(cfg) || B <= 0) return 0;
     const int chunk = clip_chunk(cfg, B);
     const long long tokens = (long long)chunk * cfg->n_frames * J;
-    return 6 * (((size_t)tokens * D * 4 + 1023) / 1024 * 1024) + module_scratch_bytes(chunk, cfg->n_frames) +
+    return 6 * (((size_t)tokens * D * 4 + 1023) / 1024 * 1024) + 3 * module_scratch_bytes(chunk, cfg->n_frames) +
            limb_tiles_bytes(chunk, cfg->n_frames, KASF_MODE_SPATIAL) + limb_tiles_bytes(chunk, cfg->n_frames, KASF_MODE_TEMPORAL);
 }
 
@@ -232,7 +232,7 @@ static int forward_impl(const kasf_config* cfg, const void* packed_dev, const fl
     {
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         const char* env = getenv("KASF_BRANCH_STREAMS");
-        const bool want = !events && T <= 128 && !(env && env[0] == '0');
+        const bool want = !events && !(env && env[0] == '0');
         if (want && cudaStreamIsCapturing(st, &cap) == cudaSuccess) {
             capturing = cap != cudaStreamCaptureStatusNone;
             side = cudaStreamCreateWithFlags(&side_s[0], cudaStreamNonBlocking) == cudaSuccess &&
@@ -250,7 +250,10 @@ static int forward_impl(const kasf_config* cfg, const void* packed_dev, const fl
         void* scr = static_cast<uint8_t*>(ws_dev) + 6 * stream_bytes;     // temporal modules, T > 128 only
         const size_t scr_bytes = module_scratch_bytes(chunk, T);
         // normalised limb rows as bf16 operand tiles (spatial / temporal tile order), shared by all layers
-        uint8_t* lt_s = static_cast<uint8_t*>(scr) + scr_bytes;
+        // (T > 128: one scratch area per branch, the branches run concurrently)
+        void* scr_g = static_cast<uint8_t*>(scr) + scr_bytes;
+        void* scr_b = static_cast<uint8_t*>(scr) + 2 * scr_bytes;
+        uint8_t* lt_s = static_cast<uint8_t*>(scr) + 3 * scr_bytes;
         uint8_t* lt_t = lt_s + limb_tiles_bytes(chunk, T, KASF_MODE_SPATIAL);
         if (limb_tiles_bytes(chunk, T, KASF_MODE_TEMPORAL) == 0) lt_t = nullptr;
         const float* x = x_dev + (size_t)b0 * T * J * 3;
@@ -260,7 +263,7 @@ static int forward_impl(const kasf_config* cfg, const void* packed_dev, const fl
         KASF_MARK();
         for (int l = 0; l < cfg->n_layers; ++l) {
             // three branches, each spatial module then temporal module (KASportsFormer.py:268-275).  The branches are
-            // independent until the fusion, so (outside the timed and split-path cases) the graph and
+            // independent until the fusion, so (outside kasf_forward_timed) the graph and
             // bone branches run on two side streams: the last, partial wave of one persistent kernel (26.7 tiles per SM
             // at B = 1024) is filled by the first CTAs of another branch's kernel instead of idling.
             const float* bone_src = l == 0 ? s.XB : s.X;
@@ -276,11 +279,11 @@ static int forward_impl(const kasf_config* cfg, const void* packed_dev, const fl
             KASF_MARK();
             if ((rc = launch_former_module(blob, l, KASF_KIND_GRAPH, KASF_MODE_SPATIAL, s.X, nullptr, s.G, nb, T, sg))) break;
             KASF_MARK();
-            if ((rc = launch_former_module(blob, l, KASF_KIND_GRAPH, KASF_MODE_TEMPORAL, s.G, nullptr, s.G, nb, T, sg, nullptr, scr, scr_bytes))) break;
+            if ((rc = launch_former_module(blob, l, KASF_KIND_GRAPH, KASF_MODE_TEMPORAL, s.G, nullptr, s.G, nb, T, sg, nullptr, scr_g, scr_bytes))) break;
             KASF_MARK();
             if ((rc = launch_former_module(blob, l, KASF_KIND_BONE, KASF_MODE_SPATIAL, bone_src, s.XL, s.Bn, nb, T, sb, nullptr, nullptr, 0, lt_s))) break;
             KASF_MARK();
-            if ((rc = launch_former_module(blob, l, KASF_KIND_BONE, KASF_MODE_TEMPORAL, s.Bn, s.XL, s.Bn, nb, T, sb, nullptr, scr, scr_bytes, lt_t))) break;
+            if ((rc = launch_former_module(blob, l, KASF_KIND_BONE, KASF_MODE_TEMPORAL, s.Bn, s.XL, s.Bn, nb, T, sb, nullptr, scr_b, scr_bytes, lt_t))) break;
             KASF_MARK();
             if (side) {
                 cudaEventRecord(side_e[1], sg);
