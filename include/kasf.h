@@ -86,6 +86,9 @@ int    kasf_pack_weights(const kasf_config* cfg, const float* image_dev, void* p
  *   rep_dev float32 [B, T, 17, 512] or NULL  (`return_rep=True` output, :342-343)
  *   ws_dev  scratch of at least kasf_workspace_bytes(cfg, B) bytes, 1024-byte aligned        */
 size_t kasf_workspace_bytes(const kasf_config* cfg, int B);
+/* (kasf_forward orders all its work on `stream`; internally the graph and bone branches of every layer run on two
+ * side streams created for the call and joined back before the next fusion -- also under stream capture, where
+ * they become part of the captured graph.  KASF_BRANCH_STREAMS=0 in the environment keeps everything on `stream`.) */
 int    kasf_forward(const kasf_config* cfg, const void* packed_dev, const float* x_dev,
                     float* y_dev, float* rep_dev, int B, void* ws_dev, size_t ws_bytes,
                     void* stream);
