@@ -69,6 +69,13 @@ constexpr uint32_t SM_TOTAL = SM_BARS + 256;
 static_assert(SM_TOTAL <= 232448, "shared memory budget");
 static_assert(MOD_VEC_BYTES == 11776, "vector block size");
 
+// Where the small per-tile arrays live and which named barriers pair the two warps of a row: the helpers below are
+// shared by this kernel (LayV1) and by the two-tiles-in-flight kernel of kasf_module_v2.cuh (its own layouts)
+struct LayV1 {
+    static constexpr uint32_t PART = SM_PART, ADJ = SM_ADJ, ROWSUM = SM_ROWSUM, RSD = SM_RSD;
+    static constexpr int PAIR_BAR = 2;
+};
+
 constexpr uint32_t TM_MIX = 0, TM_K = 128, TM_V = 256, TM_X = 384;   // mixer phase (Q lives at TM_MIX)
 constexpr uint32_t TM_H0 = 0, TM_H1 = 128, TM_OUT = 256;            // MLP phase
 
@@ -108,7 +115,8 @@ struct ModParams {
 
 __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 // the two warps (w, w+4) that share the rows of one TMEM lane quarter
-__device__ __forceinline__ void pair_sync(int warp) { asm volatile("bar.sync %0, 64;" ::"r"(2 + (warp & 3)) : "memory"); }
+template <class L = LayV1>
+__device__ __forceinline__ void pair_sync(int warp) { asm volatile("bar.sync %0, 64;" ::"r"(L::PAIR_BAR + (warp & 3)) : "memory"); }
 
 // TWICE the erf-GELU, through tanh: v (1 + erf(v / sqrt 2)) = v (1 + tanh(v (a + b v^2 + c v^4))) with a minimax
 // fit of (a, b, c) (max abs deviation from the erf form 5.6e-5 on GELU) and the hardware tanh (MUFU, rel. error
@@ -219,13 +227,14 @@ struct EpiMap {
 };
 
 // LayerNorm statistics of a row whose two halves live in two threads (exact two-pass, fp32)
+template <class L = LayV1>
 __device__ __forceinline__ void ln_stats(uint8_t* sm, const EpiMap& e, const float (&xv)[64], float& mean, float& rstd) {
-    float2* part = reinterpret_cast<float2*>(sm + SM_PART);
+    float2* part = reinterpret_cast<float2*>(sm + L::PART);
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
     for (int i = 0; i < 64; i += 4) s0 += xv[i], s1 += xv[i + 1], s2 += xv[i + 2], s3 += xv[i + 3];
     part[e.row * 2 + e.half].x = (s0 + s1) + (s2 + s3);
-    pair_sync(e.warp);
+    pair_sync<L>(e.warp);
     mean = (part[e.row * 2].x + part[e.row * 2 + 1].x) * (1.0f / D);
     float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
@@ -234,7 +243,7 @@ __device__ __forceinline__ void ln_stats(uint8_t* sm, const EpiMap& e, const flo
         q0 = fmaf(d0, d0, q0), q1 = fmaf(d1, d1, q1), q2 = fmaf(d2, d2, q2), q3 = fmaf(d3, d3, q3);
     }
     part[e.row * 2 + e.half].y = (q0 + q1) + (q2 + q3);
-    pair_sync(e.warp);
+    pair_sync<L>(e.warp);
     const float var = (part[e.row * 2].y + part[e.row * 2 + 1].y) * (1.0f / D);
     rstd = 1.0f / sqrtf(var + 1e-5f);
 }
@@ -478,10 +487,10 @@ __device__ __forceinline__ void merge_top4(float (&a)[4], const float (&b)[4]) {
 // tensor core reads and the exact fp32 remainder; hi*hi + hi*lo + lo*hi), then per row the 4th largest value
 // with multiplicity (torch.topk, graph.py:109) and A_ij = S_ij >= thr (:111).  Work item = (sequence,
 // 16-row block); the row's bit mask and degree go to smem.
-template <int MAXNT>
+template <int MAXNT, class L = LayV1>
 __device__ __forceinline__ void similarity_topk_impl(uint8_t* sm, int warp, int lane, int T, int nrows) {
-    uint32_t* adj = reinterpret_cast<uint32_t*>(sm + SM_ADJ);
-    float* rsd = reinterpret_cast<float*>(sm + SM_RSD);
+    uint32_t* adj = reinterpret_cast<uint32_t*>(sm + L::ADJ);
+    float* rsd = reinterpret_cast<float*>(sm + L::RSD);
     const int ngroups = nrows / T, mtiles = (T + 15) >> 4, nkt = (T + 7) >> 3;
     const int g8 = lane >> 2, t4 = lane & 3;
 #pragma unroll 1
@@ -621,9 +630,9 @@ __device__ __forceinline__ void similarity_topk_impl(uint8_t* sm, int warp, int 
     }
 }
 
-template <int TC>
+template <int TC, class L = LayV1>
 __device__ __forceinline__ void similarity_topk(uint8_t* sm, int warp, int lane, int T, int nrows) {
-    similarity_topk_impl<TC == 0 ? 4 : (TC == 1 ? 8 : 16)>(sm, warp, lane, T, nrows);
+    similarity_topk_impl<TC == 0 ? 4 : (TC == 1 ? 8 : 16), L>(sm, warp, lane, T, nrows);
 }
 
 // ---------------------------------------------------------------------------------------------- tile geometry
