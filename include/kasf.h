@@ -158,6 +158,16 @@ int kasf_former_module_lt(const kasf_config* cfg, const void* packed_dev, int la
 int kasf_former_module_profiled(const kasf_config* cfg, const void* packed_dev, int layer, int kind,
                                 int mode, const float* in_dev, const float* XL_dev, float* out_dev,
                                 int B, void* stream, unsigned long long* phase_cycles_dev);
+/* The same with the bone modules' limb operand from kasf_limb_tiles (limb_tiles_dev, may be null).  When the
+ * two-tiles-in-flight kernel serves the call (spatial modules, temporal ones with n_frames <= 32; bone modules only
+ * with limb tiles) the slots are: mixer group 0 wait for the gathered rows, 1 LN1, 2 Q|K|V waits and drains (graph:
+ * z hand-over), 3 attention core / adjacency + aggregation, 4 waits before the epilogue (x re-read, previous output
+ * epilogue, projection), 5 mixer epilogue; MLP group 8 wait for x1, 9 LN2, 10 fc1 waits, 11 GELU epilogues, 12 wait
+ * for the fc2 that last read the GELU buffer, 13 wait for the last fc2, 14 output epilogue. */
+int kasf_former_module_profiled_lt(const kasf_config* cfg, const void* packed_dev, int layer, int kind,
+                                   int mode, const float* in_dev, const float* XL_dev,
+                                   const void* limb_tiles_dev, float* out_dev, int B, void* stream,
+                                   unsigned long long* phase_cycles_dev);
 
 /* Adaptive fusion of the three branches (model/KASportsFormer.py:279-282). */
 int kasf_fusion(const kasf_config* cfg, const void* packed_dev, int layer, const float* att_dev,

@@ -71,6 +71,9 @@ _SIGNATURES = {
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "kasf_former_module_profiled": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_int, C.c_int, C.c_int,
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "kasf_former_module_profiled_lt": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                                 C.c_void_p]),
     "kasf_fusion": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "kasf_head": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -322,6 +325,30 @@ def former_module_phases(cfg, blob, layer, kind, mode, v, XL=None):
     B, T = v.shape[0], v.shape[1]
     tiles = (B * T + 6) // 7 if mode == "spatial" else (B * 17 + (128 // T) - 1) // (128 // T)
     return {n: prof[i].item() / tiles for i, n in enumerate(PHASES)}, tiles
+
+
+PHASES_V2 = {0: "rows_wait", 1: "ln1", 2: "qkv_wait_drain", 3: "mixer_core", 4: "epilogue_waits", 5: "mixer_epilogue",
+             8: "x1_wait", 9: "ln2", 10: "fc1_wait", 11: "gelu", 12: "gelu_buffer_wait", 13: "fc2_wait", 14: "out_epilogue"}
+
+
+def former_module_phases_v2(cfg, blob, layer, kind, mode, v, XL=None):
+    """Phase cycles of the two-tiles-in-flight kernel (bone modules through limb tiles): mean cycles per tile for
+    the mixer group (slots 0-5) and the MLP group (slots 8-14)."""
+    _require_device(v.device)
+    out = torch.empty_like(v)
+    prof = torch.zeros(32 + 2 * 6 * 600, dtype=torch.int64, device=v.device)
+    with torch.cuda.device(v.device):
+        lt = limb_tiles(cfg, XL, mode) if kind == "bone" else None
+        _check(lib().kasf_former_module_profiled_lt(C.byref(c_config(cfg)), _ptr(blob), layer, KIND[kind], MODE[mode],
+                                                    _ptr(v), _ptr(XL), _ptr(lt), _ptr(out), v.shape[0], _stream(),
+                                                    _ptr(prof)), "kasf_former_module_profiled_lt")
+        torch.cuda.synchronize()
+    B, T = v.shape[0], v.shape[1]
+    tiles = (B * T + 6) // 7 if mode == "spatial" else (B * 17 + (128 // T) - 1) // (128 // T)
+    h = prof.cpu()
+    former_module_phases_v2.trace = [e for r in range(6)
+                                     for e in h[32 + 2 * 600 * r:32 + 2 * (600 * r + int(h[24 + r]))].reshape(-1, 2).tolist()]
+    return {n: prof[i].item() / tiles for i, n in PHASES_V2.items()}, tiles
 
 
 def fusion(cfg, blob, layer, a, g, b):

@@ -191,6 +191,18 @@ int kasf_former_module_profiled(const kasf_config* cfg, const void* packed_dev, 
                                 cfg->n_frames, (cudaStream_t)stream, phase_cycles_dev);
 }
 
+int kasf_former_module_profiled_lt(const kasf_config* cfg, const void* packed_dev, int layer, int kind, int mode,
+                                   const float* in_dev, const float* XL_dev, const void* limb_tiles_dev, float* out_dev,
+                                   int B, void* stream, unsigned long long* phase_cycles_dev) {
+    int rc = config_ok(cfg);
+    if (rc) return rc;
+    if (!packed_dev || !in_dev || !out_dev || !phase_cycles_dev || B < 0 || layer < 0 || layer >= cfg->n_layers)
+        return KASF_EINVAL;
+    if ((rc = device_ok())) return rc;
+    return launch_former_module((const uint8_t*)packed_dev, layer, kind, mode, in_dev, XL_dev, out_dev, B,
+                                cfg->n_frames, (cudaStream_t)stream, phase_cycles_dev, nullptr, 0, limb_tiles_dev);
+}
+
 int kasf_fusion(const kasf_config* cfg, const void* packed_dev, int layer, const float* att_dev,
                 const float* graph_dev, const float* bone_dev, float* out_dev, int B, void* stream) {
     int rc = config_ok(cfg);

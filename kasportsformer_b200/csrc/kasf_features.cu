@@ -123,7 +123,7 @@ int launch_features(const uint8_t* blob, const float* x, float* bone, float* lim
                     long long frames, cudaStream_t st) {
     if (frames <= 0) return KASF_OK;
     const long long nblk = (frames + FR - 1) / FR;
-    const int grid = (int)min(nblk, (long long)148 * 8);
+    const int grid = (int)min(nblk, (long long)sm_count() * 8);
     features_kernel<<<grid, FEAT_THREADS, 0, st>>>(blob, x, bone, limb, X, XB, XL, frames);
     return cuda_status();
 }

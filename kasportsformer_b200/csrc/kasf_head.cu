@@ -78,7 +78,7 @@ int launch_fusion(const uint8_t* blob, int layer, const float* a, const float* g
                   long long tokens, cudaStream_t st) {
     if (tokens <= 0) return KASF_OK;
     const float* fw = reinterpret_cast<const float*>(blob + fusion_off(layer));
-    const int grid = (int)min((tokens + 7) / 8, (long long)148 * 16);
+    const int grid = (int)min((tokens + 7) / 8, (long long)sm_count() * 16);
     fusion_kernel<<<grid, 256, 0, st>>>(fw, a, g, b, out, tokens);
     return cuda_status();
 }
@@ -187,7 +187,7 @@ int launch_head(const uint8_t* blob, const float* X, float* y, float* rep, long 
     if (tokens <= 0) return KASF_OK;
     cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM);
     const long long ntiles = (tokens + HT - 1) / HT;
-    const int grid = (int)min(ntiles, (long long)148 * 2);
+    const int grid = (int)min(ntiles, (long long)sm_count() * 2);
     head_kernel<<<grid, 256, HEAD_SMEM, st>>>(reinterpret_cast<const float*>(blob), X, y, rep, tokens);
     return cuda_status();
 }

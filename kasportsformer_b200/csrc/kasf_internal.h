@@ -15,6 +15,14 @@ inline int cuda_status() {
     return e == cudaSuccess ? KASF_OK : -(1000 + (int)e);
 }
 
+// SMs of the current device (persistent kernels launch one CTA per SM)
+inline int sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+        return 148;
+    return n;
+}
+
 int pack_weights(const kasf_config* cfg, const float* image, void* packed, size_t cap, cudaStream_t st);
 
 int launch_features(const uint8_t* blob, const float* x, float* bone, float* limb, float* X, float* XB, float* XL,

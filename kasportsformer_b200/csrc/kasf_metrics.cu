@@ -26,7 +26,7 @@ __global__ void flip_kernel(const float* __restrict__ in, float* __restrict__ ou
 int launch_flip(const float* in, float* out, long long frames, cudaStream_t st) {
     if (frames <= 0) return KASF_OK;
     const long long n = frames * 51;
-    flip_kernel<<<(int)min((n + 255) / 256, (long long)148 * 16), 256, 0, st>>>(in, out, n);
+    flip_kernel<<<(int)min((n + 255) / 256, (long long)sm_count() * 16), 256, 0, st>>>(in, out, n);
     return cuda_status();
 }
 
@@ -240,7 +240,7 @@ int launch_metrics(int T, const float* pred, const float* pred_flip, const float
     if (B <= 0) return KASF_OK;
     if (T < 1 || n_actions < 1) return KASF_EINVAL;
     const long long frames = (long long)B * T;
-    const int grid = (int)min((frames + 127) / 128, (long long)148 * 8);
+    const int grid = (int)min((frames + 127) / 128, (long long)sm_count() * 8);
     metrics_kernel<<<grid, 128, 0, st>>>(T, pred, pred_flip, gt, res, factor, action, n_actions, sums, per_frame, frames);
     return cuda_status();
 }

@@ -31,6 +31,7 @@
 //                              LN partials, adjacency bit masks, degrees, barriers
 // Tensor memory columns:       0..127 Q -> mixer output -> hidden chunk 0 | 128..255 K -> hidden chunk 1
 //                              256..383 V -> fc2 accumulator             | 384..511 residual rows X
+#include <cstdlib>
 #include <cstring>
 
 #include "kasf_internal.h"
@@ -1272,7 +1273,8 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
 
 template <int KIND, int MODE, int TC>
 static int launch_one(const ModParams& p, cudaStream_t st) {
-    const int grid = p.ntiles < 148 ? p.ntiles : 148;
+    const int sms = sm_count();
+    const int grid = p.ntiles < sms ? p.ntiles : sms;
     if constexpr (TC == 0 && MODE != KASF_MODE_LONG) {     // profiling hook: short sequences only
         if (p.prof) {
             cudaFuncSetAttribute(former_module_kernel<KIND, MODE, TC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
@@ -1284,6 +1286,8 @@ static int launch_one(const ModParams& p, cudaStream_t st) {
     former_module_kernel<KIND, MODE, TC><<<grid, MOD_THREADS, SM_TOTAL, st>>>(p);
     return cuda_status();
 }
+
+#include "kasf_module_v2.cuh"
 
 // ============================================================================================== split path (T > 128)
 // A temporal sequence longer than one 128-row tile (T = 243) does not fit the fused kernel's "a tile owns whole
@@ -1827,7 +1831,7 @@ int launch_limb_tiles(const float* XL, void* tiles, int B, int T, int mode, cuda
     p.xl = XL;
     p.B = B, p.T = T;
     mode_tiling(p, mode);
-    const int grid = p.ntiles < 148 * 8 ? p.ntiles : 148 * 8;
+    const int grid = p.ntiles < sm_count() * 8 ? p.ntiles : sm_count() * 8;
     if (mode == KASF_MODE_SPATIAL) limb_tiles_kernel<KASF_MODE_SPATIAL><<<grid, 256, 0, st>>>(p, static_cast<uint8_t*>(tiles));
     else limb_tiles_kernel<KASF_MODE_TEMPORAL><<<grid, 256, 0, st>>>(p, static_cast<uint8_t*>(tiles));
     return cuda_status();
@@ -1863,6 +1867,16 @@ int launch_former_module(const uint8_t* blob, int layer, int kind, int mode, con
         p.groups_per_tile = 128 / T;
         p.ntiles = (int)(((long long)B * J + p.groups_per_tile - 1) / p.groups_per_tile);
         tc = T <= 32 ? 0 : (T <= 64 ? 1 : 2);
+    }
+    // two tiles in flight per SM (kasf_module_v2.cuh): short groups, bone modules fed from limb tiles.
+    // KASF_ONE_TILE=1 selects the one-tile kernel everywhere (A/B measurements, the stage tests cover both)
+    static const bool one_tile = [] { const char* e = getenv("KASF_ONE_TILE"); return e && e[0] == '1'; }();
+    if (tc == 0 && !one_tile && (kind != KASF_KIND_BONE || p.xlt)) {
+        const int sms = sm_count();
+#define KASF_CASE2(K, M) \
+    if (kind == K && mode == M) return v2::launch_v2<K, M>(p, st, sms);
+        KASF_CASE2(0, 0) KASF_CASE2(0, 1) KASF_CASE2(1, 0) KASF_CASE2(1, 1) KASF_CASE2(2, 0) KASF_CASE2(2, 1)
+#undef KASF_CASE2
     }
 #define KASF_CASE(K, M, C) \
     if (kind == K && mode == M && tc == C) return launch_one<K, M, C>(p, st);
