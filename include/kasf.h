@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define KASF_VERSION 1
+#define KASF_VERSION 2
 
 #define KASF_OK        0
 #define KASF_EINVAL   -1   /* null pointer / bad enum / misaligned buffer                     */
@@ -38,7 +38,7 @@ extern "C" {
 /* Model hyper-parameters: the YAML model keys of the reference (configs/*.yaml:66-92) that reach
  * KASportsFormer.__init__ (model/KASportsFormer.py:291-295).  This build implements
  * dim_feat=128, num_heads=8, mlp_ratio=4, dim_rep=512, num_joints=17, dim_in=dim_out=3,
- * neighbour_num=4, n_frames in [3,243]; anything else -> KASF_ESHAPE. */
+ * neighbour_num=4, n_frames in [4,243]; anything else -> KASF_ESHAPE. */
 typedef struct kasf_config {
     int32_t n_layers;
     int32_t n_frames;
@@ -84,14 +84,44 @@ int    kasf_pack_weights(const kasf_config* cfg, const float* image_dev, void* p
  *   x_dev   float32 [B, T, 17, 3] contiguous (x, y, confidence)
  *   y_dev   float32 [B, T, 17, 3]            (3D pose, normalised units)
  *   rep_dev float32 [B, T, 17, 512] or NULL  (`return_rep=True` output, :342-343)
- *   ws_dev  scratch of at least kasf_workspace_bytes(cfg, B) bytes, 1024-byte aligned        */
+ *   ws_dev  scratch of at least kasf_workspace_bytes(cfg, B) bytes, 256-byte aligned         */
 size_t kasf_workspace_bytes(const kasf_config* cfg, int B);
-/* (kasf_forward orders all its work on `stream`; internally the graph and bone branches of every layer run on two
- * side streams created for the call and joined back before the next fusion -- also under stream capture, where
- * they become part of the captured graph.  KASF_BRANCH_STREAMS=0 in the environment keeps everything on `stream`.) */
+/* kasf_forward enqueues all its work on `stream`, one kernel after the other, fast precision: the stateless form. */
 int    kasf_forward(const kasf_config* cfg, const void* packed_dev, const float* x_dev,
                     float* y_dev, float* rep_dev, int B, void* ws_dev, size_t ws_bytes,
                     void* stream);
+
+/* Forward with options.
+ *   precision  KASF_PRECISION_FAST: bf16 tensor-core operands with fp32 accumulation, fp16 MLP hidden tile, tanh-form
+ *              GELU (max deviation 5.6e-5 from erf); fp32 residual stream, statistics, softmax, similarity, head.
+ *              KASF_PRECISION_EXACT: the reference's arithmetic -- fp32 FMA everywhere, erf GELU -- on CUDA cores
+ *              (no tensor cores): for checking a checkpoint's accuracy, an order of magnitude slower.  Needs the
+ *              fp32 weight image (`image_dev`, the array kasf_pack_weights consumed) instead of the packed blob and
+ *              kasf_workspace_bytes_ex(cfg, B, KASF_PRECISION_EXACT) bytes of workspace.
+ *   flags      KASF_FLAG_TWO_TILES: the two-tiles-in-flight FormerModule kernel where it applies (spatial modules,
+ *              temporal ones with n_frames <= 32) -- parity-tested, currently slower than the default kernel.
+ *   ctx        NULL, or a kasf_forward_ctx: two side streams and three events, created once by the caller for a
+ *              (device, host thread) pair.  With a context the graph and bone branches of every layer run on the side
+ *              streams (forked after the previous fusion, joined before the next one): the last, partial wave of one
+ *              persistent kernel is filled by the first CTAs of another branch's kernel.  Also valid under stream
+ *              capture (the fork / join becomes part of the captured graph; keep the context alive with the graph).
+ *              The library itself keeps no state and reads no environment variables. */
+#define KASF_PRECISION_FAST  0
+#define KASF_PRECISION_EXACT 1
+#define KASF_FLAG_TWO_TILES  1u
+typedef struct kasf_forward_ctx kasf_forward_ctx;
+kasf_forward_ctx* kasf_ctx_create(void);                 /* on the current device; NULL on failure */
+void              kasf_ctx_destroy(kasf_forward_ctx* ctx);
+typedef struct kasf_forward_opts {
+    int32_t precision;
+    uint32_t flags;
+    kasf_forward_ctx* ctx;
+    const float* image_dev;      /* KASF_PRECISION_EXACT only */
+} kasf_forward_opts;
+size_t kasf_workspace_bytes_ex(const kasf_config* cfg, int B, int precision);
+int    kasf_forward_ex(const kasf_config* cfg, const void* packed_dev, const float* x_dev,
+                       float* y_dev, float* rep_dev, int B, void* ws_dev, size_t ws_bytes,
+                       void* stream, const kasf_forward_opts* opts /* NULL: defaults */);
 /* Number of kernel launches one kasf_forward(B) enqueues (for bench accounting). */
 int    kasf_forward_launches(const kasf_config* cfg, int B);
 /* Number of timing marks of kasf_forward_timed: one per stage (features, every FormerModule, every fusion,
@@ -148,6 +178,12 @@ int kasf_limb_tiles(const kasf_config* cfg, const float* XL_dev, void* limb_tile
 int kasf_former_module_lt(const kasf_config* cfg, const void* packed_dev, int layer, int kind, int mode,
                           const float* in_dev, const float* XL_dev, const void* limb_tiles_dev,
                           float* out_dev, int B, void* scratch_dev, size_t scratch_bytes, void* stream);
+/* The same with `flags` (KASF_FLAG_TWO_TILES: returns KASF_ESHAPE where that kernel does not apply -- temporal
+ * modules with n_frames > 32, bone modules without limb tiles). */
+int kasf_former_module_ex(const kasf_config* cfg, const void* packed_dev, int layer, int kind, int mode,
+                          const float* in_dev, const float* XL_dev, const void* limb_tiles_dev,
+                          float* out_dev, int B, void* scratch_dev, size_t scratch_bytes, uint32_t flags,
+                          void* stream);
 
 /* Profiling hook (own kernel instantiations, n_frames <= 32 and fused path only; otherwise the counters stay zero):
  * same launch, additionally accumulating (atomicAdd by thread 0 of every CTA) the SM cycles

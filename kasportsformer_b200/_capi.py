@@ -27,6 +27,14 @@ class KasfConfig(C.Structure):
                                           "mlp_ratio", "num_joints", "neighbour_num")]
 
 
+class KasfForwardOpts(C.Structure):
+    _fields_ = [("precision", C.c_int32), ("flags", C.c_uint32), ("ctx", C.c_void_p), ("image_dev", C.c_void_p)]
+
+
+PRECISION = {"fast": 0, "exact": 1}
+FLAG_TWO_TILES = 1
+
+
 class KasfError(RuntimeError):
     pass
 
@@ -71,6 +79,14 @@ _SIGNATURES = {
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "kasf_former_module_profiled": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_int, C.c_int, C.c_int,
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "kasf_ctx_create": (C.c_void_p, []),
+    "kasf_ctx_destroy": (None, [C.c_void_p]),
+    "kasf_workspace_bytes_ex": (C.c_size_t, [C.POINTER(KasfConfig), C.c_int, C.c_int]),
+    "kasf_forward_ex": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                  C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "kasf_former_module_ex": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_uint32,
+                                        C.c_void_p]),
     "kasf_former_module_profiled_lt": (C.c_int, [C.POINTER(KasfConfig), C.c_void_p, C.c_int, C.c_int, C.c_int,
                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                                  C.c_void_p]),
@@ -178,7 +194,8 @@ def build_weight_image(cfg: dict, state: Dict[str, torch.Tensor]) -> torch.Tenso
     return img
 
 
-def pack_state(cfg: dict, state: Dict[str, torch.Tensor], device: torch.device) -> torch.Tensor:
+def pack_state(cfg: dict, state: Dict[str, torch.Tensor], device: torch.device, keep_image: bool = False):
+    """The kernel-ready blob (and, with keep_image, the fp32 weight image on the device: precision="exact" reads it)."""
     _require_device(device)
     l, cc = lib(), c_config(cfg)
     # assemble on the device the tensors live on if they already are there (no host round trip)
@@ -188,35 +205,92 @@ def pack_state(cfg: dict, state: Dict[str, torch.Tensor], device: torch.device) 
     with torch.cuda.device(device):
         _check(l.kasf_pack_weights(C.byref(cc), _ptr(img), _ptr(blob), nbytes, _stream()), "kasf_pack_weights")
         torch.cuda.current_stream().synchronize()   # img may be freed after return
-    return blob
+    return (blob, img) if keep_image else blob
 
 
 # --- forward + stages ----------------------------------------------------------------------------
+# Per (device, host thread, stream) state of the callers of this module: the workspace and the forward context (two
+# side streams + three events, kasf_ctx_create).  nn.DataParallel calls forward from one thread per device: the key
+# keeps those callers apart, the lock protects the dictionaries themselves.
 _ws_cache: Dict[tuple, torch.Tensor] = {}
+_ctx_cache: Dict[tuple, "ForwardContext"] = {}
+_state_lock = threading.Lock()
 
 
-def _workspace(cfg: dict, B: int, device: torch.device) -> torch.Tensor:
-    n = lib().kasf_workspace_bytes(C.byref(c_config(cfg)), B)
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-    ws = _ws_cache.get(key)
-    if ws is None or ws.numel() < n:
-        ws = torch.empty(n, dtype=torch.uint8, device=device)
-        _ws_cache[key] = ws
+class ForwardContext:
+    """Owner of a kasf_forward_ctx (side streams + events for the branch-parallel forward)."""
+
+    def __init__(self, device: torch.device):
+        with torch.cuda.device(device):
+            self.handle = lib().kasf_ctx_create()
+        if not self.handle:
+            raise KasfError("kasf_ctx_create failed")
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                lib().kasf_ctx_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def _caller_key(device: torch.device):
+    return (device.index, threading.get_ident(), torch.cuda.current_stream(device).cuda_stream)
+
+
+def _workspace(cfg: dict, B: int, device: torch.device, precision: int = 0) -> torch.Tensor:
+    n = lib().kasf_workspace_bytes_ex(C.byref(c_config(cfg)), B, precision)
+    key = _caller_key(device)
+    with _state_lock:
+        ws = _ws_cache.get(key)
+        if ws is None or ws.numel() < n:
+            ws = torch.empty(n, dtype=torch.uint8, device=device)
+            _ws_cache[key] = ws
     return ws
 
 
-def forward(cfg: dict, blob: torch.Tensor, x: torch.Tensor, return_rep: bool = False) -> torch.Tensor:
+def _context(device: torch.device) -> ForwardContext:
+    key = _caller_key(device)
+    with _state_lock:
+        ctx = _ctx_cache.get(key)
+        if ctx is None:
+            ctx = _ctx_cache[key] = ForwardContext(device)
+    return ctx
+
+
+def _launch_forward(cfg, blob, x, y, rep, ws, ctx, precision=0, flags=0, image=None):
+    opts = KasfForwardOpts(precision, flags, ctx.handle if ctx is not None else None, _ptr(image))
+    _check(lib().kasf_forward_ex(C.byref(c_config(cfg)), _ptr(blob), _ptr(x), _ptr(y), _ptr(rep), x.shape[0],
+                                 _ptr(ws), ws.numel(), _stream(), C.byref(opts)), "kasf_forward_ex")
+
+
+def forward(cfg: dict, blob: torch.Tensor, x: torch.Tensor, return_rep: bool = False, precision: str = "fast",
+            image: Optional[torch.Tensor] = None, two_tiles: bool = False, ws: Optional[torch.Tensor] = None,
+            ctx: Optional[ForwardContext] = None, branch_streams: bool = True) -> torch.Tensor:
+    """kasf_forward_ex.  precision "exact" needs `image` (the fp32 weight image on the device, pack_state(...,
+    keep_image=True)).  `ws` / `ctx`: caller-owned workspace and context (CUDA-graph capture); default: cached per
+    (device, thread, stream)."""
     _require_device(x.device)
     B, T = x.shape[0], x.shape[1]
     y = torch.empty(B, T, 17, 3, dtype=torch.float32, device=x.device)
     rep = torch.empty(B, T, 17, cfg["dim_rep"], dtype=torch.float32, device=x.device) if return_rep else None
     if B == 0:
         return rep if return_rep else y
+    prec = PRECISION[precision]
+    if prec == 1 and image is None:
+        raise KasfError('precision="exact" needs the fp32 weight image')
     with torch.cuda.device(x.device):
-        ws = _workspace(cfg, B, x.device)
-        _check(lib().kasf_forward(C.byref(c_config(cfg)), _ptr(blob), _ptr(x), _ptr(y), _ptr(rep), B,
-                                  _ptr(ws), ws.numel(), _stream()), "kasf_forward")
+        if ws is None:
+            ws = _workspace(cfg, B, x.device, prec)
+        if ctx is None and branch_streams and prec == 0:
+            ctx = _context(x.device)
+        _launch_forward(cfg, blob, x, y, rep, ws, ctx, prec, FLAG_TWO_TILES if two_tiles else 0, image)
     return rep if return_rep else y
+
+
+def workspace_bytes(cfg: dict, B: int, precision: str = "fast") -> int:
+    return lib().kasf_workspace_bytes_ex(C.byref(c_config(cfg)), B, PRECISION[precision])
 
 
 class LaunchTimer:
@@ -236,14 +310,14 @@ class LaunchTimer:
             lib().kasf_event_destroy(e)
 
 
-def forward_into(cfg: dict, blob: torch.Tensor, x: torch.Tensor, y: torch.Tensor, timer: "LaunchTimer" = None):
+def forward_into(cfg: dict, blob: torch.Tensor, x: torch.Tensor, y: torch.Tensor, timer: "LaunchTimer" = None,
+                 two_tiles: bool = False):
     """Forward into a preallocated output (bench loop: no allocation inside the timed region)."""
     B = x.shape[0]
     with torch.cuda.device(x.device):
         ws = _workspace(cfg, B, x.device)
         if timer is None:
-            _check(lib().kasf_forward(C.byref(c_config(cfg)), _ptr(blob), _ptr(x), _ptr(y), None, B,
-                                      _ptr(ws), ws.numel(), _stream()), "kasf_forward")
+            _launch_forward(cfg, blob, x, y, None, ws, _context(x.device), 0, FLAG_TWO_TILES if two_tiles else 0)
         else:
             _check(lib().kasf_forward_timed(C.byref(c_config(cfg)), _ptr(blob), _ptr(x), _ptr(y), None, B,
                                             _ptr(ws), ws.numel(), _stream(), timer.events, timer.n),
@@ -286,16 +360,22 @@ def limb_tiles(cfg, XL, mode):
     return tiles
 
 
-def former_module(cfg, blob, layer, kind, mode, v, XL=None, out=None, use_limb_tiles=False):
+def former_module(cfg, blob, layer, kind, mode, v, XL=None, out=None, use_limb_tiles=False, two_tiles=False):
     """One FormerModule.  use_limb_tiles: bone modules take their K|V operand from pre-normalised limb tiles (the
-    path kasf_forward uses) instead of normalising XL inside the kernel."""
+    path kasf_forward uses) instead of normalising XL inside the kernel.  two_tiles: the two-tiles-in-flight kernel
+    (KASF_FLAG_TWO_TILES; bone modules then always through limb tiles)."""
     _require_device(v.device)
     B = v.shape[0]
     out = torch.empty_like(v) if out is None else out
     with torch.cuda.device(v.device):
         nscr = lib().kasf_module_scratch_bytes(C.byref(c_config(cfg)), B) if mode == "temporal" else 0
         scr = torch.empty(max(nscr, 256), dtype=torch.uint8, device=v.device)
-        if use_limb_tiles and kind == "bone":
+        if two_tiles:
+            lt = limb_tiles(cfg, XL, mode) if kind == "bone" else None
+            _check(lib().kasf_former_module_ex(C.byref(c_config(cfg)), _ptr(blob), layer, KIND[kind], MODE[mode],
+                                               _ptr(v), _ptr(XL), _ptr(lt), _ptr(out), B, _ptr(scr), nscr,
+                                               FLAG_TWO_TILES, _stream()), "kasf_former_module_ex")
+        elif use_limb_tiles and kind == "bone":
             lt = limb_tiles(cfg, XL, mode)
             _check(lib().kasf_former_module_lt(C.byref(c_config(cfg)), _ptr(blob), layer, KIND[kind], MODE[mode],
                                                _ptr(v), _ptr(XL), _ptr(lt), _ptr(out), B, _ptr(scr), nscr, _stream()),

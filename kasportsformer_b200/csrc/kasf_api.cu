@@ -1,6 +1,7 @@
 // kasf_api.cu -- extern "C" entry points of libkasf.so (declared in include/kasf.h) and the
 // orchestration of the forward pass (reference model/KASportsFormer.py:320-347).
 #include <cstdlib>
+#include <new>
 
 #include "kasf_internal.h"
 
@@ -38,7 +39,37 @@ Streams carve(void* ws, long long tokens) {
 
 }  // namespace
 
+// side streams + events of one caller (device, host thread): see kasf.h
+struct kasf_forward_ctx {
+    cudaStream_t s[2];
+    cudaEvent_t e[3];
+};
+
 extern "C" {
+
+kasf_forward_ctx* kasf_ctx_create(void) {
+    kasf_forward_ctx* c = new (std::nothrow) kasf_forward_ctx();
+    if (!c) return nullptr;
+    bool ok = true;
+    for (int i = 0; i < 2; ++i) c->s[i] = nullptr;
+    for (int i = 0; i < 3; ++i) c->e[i] = nullptr;
+    for (int i = 0; i < 2 && ok; ++i) ok = cudaStreamCreateWithFlags(&c->s[i], cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 3 && ok; ++i) ok = cudaEventCreateWithFlags(&c->e[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        kasf_ctx_destroy(c);
+        return nullptr;
+    }
+    return c;
+}
+
+void kasf_ctx_destroy(kasf_forward_ctx* c) {
+    if (!c) return;
+    for (int i = 0; i < 3; ++i)
+        if (c->e[i]) cudaEventDestroy(c->e[i]);
+    for (int i = 0; i < 2; ++i)
+        if (c->s[i]) cudaStreamDestroy(c->s[i]);
+    delete c;
+}
 
 int kasf_version(void) { return KASF_VERSION; }
 
@@ -105,6 +136,11 @@ size_t kasf_workspace_bytes(const kasf_config* cfg, int B) {
     const long long tokens = (long long)chunk * cfg->n_frames * J;
     return 6 * (((size_t)tokens * D * 4 + 1023) / 1024 * 1024) + 3 * module_scratch_bytes(chunk, cfg->n_frames) +
            limb_tiles_bytes(chunk, cfg->n_frames, KASF_MODE_SPATIAL) + limb_tiles_bytes(chunk, cfg->n_frames, KASF_MODE_TEMPORAL);
+}
+
+size_t kasf_workspace_bytes_ex(const kasf_config* cfg, int B, int precision) {
+    if (precision == KASF_PRECISION_EXACT) return (config_ok(cfg) || B <= 0) ? 0 : exact_workspace_bytes(cfg, B);
+    return kasf_workspace_bytes(cfg, B);
 }
 
 size_t kasf_module_scratch_bytes(const kasf_config* cfg, int B) {
@@ -174,6 +210,17 @@ int kasf_former_module_lt(const kasf_config* cfg, const void* packed_dev, int la
                                 cfg->n_frames, (cudaStream_t)stream, nullptr, scratch_dev, scratch_bytes, limb_tiles_dev);
 }
 
+int kasf_former_module_ex(const kasf_config* cfg, const void* packed_dev, int layer, int kind, int mode,
+                          const float* in_dev, const float* XL_dev, const void* limb_tiles_dev, float* out_dev, int B,
+                          void* scratch_dev, size_t scratch_bytes, uint32_t flags, void* stream) {
+    int rc = config_ok(cfg);
+    if (rc) return rc;
+    if (!packed_dev || !in_dev || !out_dev || B < 0 || layer < 0 || layer >= cfg->n_layers) return KASF_EINVAL;
+    if ((rc = device_ok())) return rc;
+    return launch_former_module((const uint8_t*)packed_dev, layer, kind, mode, in_dev, XL_dev, out_dev, B,
+                                cfg->n_frames, (cudaStream_t)stream, nullptr, scratch_dev, scratch_bytes, limb_tiles_dev, flags);
+}
+
 int kasf_former_module(const kasf_config* cfg, const void* packed_dev, int layer, int kind, int mode,
                        const float* in_dev, const float* XL_dev, float* out_dev, int B, void* stream) {
     return kasf_former_module_ws(cfg, packed_dev, layer, kind, mode, in_dev, XL_dev, out_dev, B, nullptr, 0, stream);
@@ -225,36 +272,35 @@ int kasf_head(const kasf_config* cfg, const void* packed_dev, const float* X_dev
 }
 
 static int forward_impl(const kasf_config* cfg, const void* packed_dev, const float* x_dev, float* y_dev,
-                        float* rep_dev, int B, void* ws_dev, size_t ws_bytes, void* stream, void** events) {
+                        float* rep_dev, int B, void* ws_dev, size_t ws_bytes, void* stream, void** events,
+                        const kasf_forward_opts* opts) {
     int rc = config_ok(cfg);
     if (rc) return rc;
-    if (!packed_dev || !x_dev || (!y_dev && !rep_dev) || !ws_dev || B < 0) return KASF_EINVAL;
+    const int precision = opts ? opts->precision : KASF_PRECISION_FAST;
+    if (precision != KASF_PRECISION_FAST && precision != KASF_PRECISION_EXACT) return KASF_EINVAL;
+    if (!x_dev || (!y_dev && !rep_dev) || !ws_dev || B < 0) return KASF_EINVAL;
     if (((uintptr_t)ws_dev & 255) != 0) return KASF_EINVAL;
-    if (ws_bytes < kasf_workspace_bytes(cfg, B)) return KASF_ENOMEM;
+    if (ws_bytes < kasf_workspace_bytes_ex(cfg, B, precision)) return KASF_ENOMEM;
     if ((rc = device_ok())) return rc;
-    const uint8_t* blob = (const uint8_t*)packed_dev;
     cudaStream_t st = (cudaStream_t)stream;
+    if (precision == KASF_PRECISION_EXACT) {
+        if (!opts->image_dev || !packed_dev || events) return KASF_EINVAL;
+        return exact_forward(cfg, opts->image_dev, (const uint8_t*)packed_dev, x_dev, y_dev, rep_dev, B, ws_dev, ws_bytes, st);
+    }
+    if (!packed_dev) return KASF_EINVAL;
+    const uint8_t* blob = (const uint8_t*)packed_dev;
     const int T = cfg->n_frames;
     const int chunk = clip_chunk(cfg, B);
+    const unsigned flags = opts ? opts->flags : 0u;
+    // the two-tiles kernel where it applies (spatial modules; temporal ones with short sequences)
+    const unsigned fl_s = flags & KASF_FLAG_TWO_TILES, fl_t = T <= 32 ? fl_s : 0u;
     int ev = 0;
-    // side streams for the graph / bone branches (see the layer loop); created per call, the library keeps no state
-    bool side = false, capturing = false;
-    cudaStream_t side_s[2] = {nullptr, nullptr};
-    cudaEvent_t side_e[3] = {nullptr, nullptr, nullptr};
-    {
-        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-        const char* env = getenv("KASF_BRANCH_STREAMS");
-        const bool want = !events && !(env && env[0] == '0');
-        if (want && cudaStreamIsCapturing(st, &cap) == cudaSuccess) {
-            capturing = cap != cudaStreamCaptureStatusNone;
-            side = cudaStreamCreateWithFlags(&side_s[0], cudaStreamNonBlocking) == cudaSuccess &&
-                   cudaStreamCreateWithFlags(&side_s[1], cudaStreamNonBlocking) == cudaSuccess;
-            for (int i = 0; i < 3 && side; ++i) side = cudaEventCreateWithFlags(&side_e[i], cudaEventDisableTiming) == cudaSuccess;
-        }
-    }
+    // side streams for the graph / bone branches (see the layer loop): the caller's context, never under per-stage timing
+    kasf_forward_ctx* ctx = (opts && !events) ? opts->ctx : nullptr;
+    bool forked = false;
 #define KASF_MARK() do { if (events) cudaEventRecord((cudaEvent_t)events[ev++], st); } while (0)
     KASF_MARK();
-    for (int b0 = 0; b0 < B; b0 += chunk) {
+    for (int b0 = 0; b0 < B && !rc; b0 += chunk) {
         const int nb = B - b0 < chunk ? B - b0 : chunk;
         const long long tokens = (long long)nb * T * J;
         Streams s = carve(ws_dev, (long long)chunk * T * J);
@@ -273,36 +319,42 @@ static int forward_impl(const kasf_config* cfg, const void* packed_dev, const fl
         if ((rc = launch_limb_tiles(s.XL, lt_s, nb, T, KASF_MODE_SPATIAL, st))) break;
         if ((rc = launch_limb_tiles(s.XL, lt_t, nb, T, KASF_MODE_TEMPORAL, st))) break;
         KASF_MARK();
-        for (int l = 0; l < cfg->n_layers; ++l) {
+        for (int l = 0; l < cfg->n_layers && !rc; ++l) {
             // three branches, each spatial module then temporal module (KASportsFormer.py:268-275).  The branches are
-            // independent until the fusion, so (outside kasf_forward_timed) the graph and
-            // bone branches run on two side streams: the last, partial wave of one persistent kernel (26.7 tiles per SM
-            // at B = 1024) is filled by the first CTAs of another branch's kernel instead of idling.
+            // independent until the fusion, so with a context the graph and bone branches run on its two side
+            // streams: the last, partial wave of one persistent kernel (26.7 tiles per SM at B = 1024) is filled by the
+            // first CTAs of another branch's kernel instead of idling.
             const float* bone_src = l == 0 ? s.XB : s.X;
-            cudaStream_t sg = side ? side_s[0] : st, sb = side ? side_s[1] : st;
-            if (side) {
-                cudaEventRecord(side_e[0], st);              // X of this layer is final
-                cudaStreamWaitEvent(sg, side_e[0], 0);
-                cudaStreamWaitEvent(sb, side_e[0], 0);
+            cudaStream_t sg = st, sb = st;
+            if (ctx && cudaEventRecord(ctx->e[0], st) == cudaSuccess &&               // X of this layer is final
+                cudaStreamWaitEvent(ctx->s[0], ctx->e[0], 0) == cudaSuccess &&
+                cudaStreamWaitEvent(ctx->s[1], ctx->e[0], 0) == cudaSuccess) {
+                sg = ctx->s[0], sb = ctx->s[1];
+                forked = true;
             }
-            if ((rc = launch_former_module(blob, l, KASF_KIND_ATTENTION, KASF_MODE_SPATIAL, s.X, nullptr, s.A, nb, T, st))) break;
-            KASF_MARK();
-            if ((rc = launch_former_module(blob, l, KASF_KIND_ATTENTION, KASF_MODE_TEMPORAL, s.A, nullptr, s.A, nb, T, st, nullptr, scr, scr_bytes))) break;
-            KASF_MARK();
-            if ((rc = launch_former_module(blob, l, KASF_KIND_GRAPH, KASF_MODE_SPATIAL, s.X, nullptr, s.G, nb, T, sg))) break;
-            KASF_MARK();
-            if ((rc = launch_former_module(blob, l, KASF_KIND_GRAPH, KASF_MODE_TEMPORAL, s.G, nullptr, s.G, nb, T, sg, nullptr, scr_g, scr_bytes))) break;
-            KASF_MARK();
-            if ((rc = launch_former_module(blob, l, KASF_KIND_BONE, KASF_MODE_SPATIAL, bone_src, s.XL, s.Bn, nb, T, sb, nullptr, nullptr, 0, lt_s))) break;
-            KASF_MARK();
-            if ((rc = launch_former_module(blob, l, KASF_KIND_BONE, KASF_MODE_TEMPORAL, s.Bn, s.XL, s.Bn, nb, T, sb, nullptr, scr_b, scr_bytes, lt_t))) break;
-            KASF_MARK();
-            if (side) {
-                cudaEventRecord(side_e[1], sg);
-                cudaEventRecord(side_e[2], sb);
-                cudaStreamWaitEvent(st, side_e[1], 0);
-                cudaStreamWaitEvent(st, side_e[2], 0);
+            do {
+                if ((rc = launch_former_module(blob, l, KASF_KIND_ATTENTION, KASF_MODE_SPATIAL, s.X, nullptr, s.A, nb, T, st, nullptr, nullptr, 0, nullptr, fl_s))) break;
+                KASF_MARK();
+                if ((rc = launch_former_module(blob, l, KASF_KIND_ATTENTION, KASF_MODE_TEMPORAL, s.A, nullptr, s.A, nb, T, st, nullptr, scr, scr_bytes, nullptr, fl_t))) break;
+                KASF_MARK();
+                if ((rc = launch_former_module(blob, l, KASF_KIND_GRAPH, KASF_MODE_SPATIAL, s.X, nullptr, s.G, nb, T, sg, nullptr, nullptr, 0, nullptr, fl_s))) break;
+                KASF_MARK();
+                if ((rc = launch_former_module(blob, l, KASF_KIND_GRAPH, KASF_MODE_TEMPORAL, s.G, nullptr, s.G, nb, T, sg, nullptr, scr_g, scr_bytes, nullptr, fl_t))) break;
+                KASF_MARK();
+                if ((rc = launch_former_module(blob, l, KASF_KIND_BONE, KASF_MODE_SPATIAL, bone_src, s.XL, s.Bn, nb, T, sb, nullptr, nullptr, 0, lt_s, fl_s))) break;
+                KASF_MARK();
+                if ((rc = launch_former_module(blob, l, KASF_KIND_BONE, KASF_MODE_TEMPORAL, s.Bn, s.XL, s.Bn, nb, T, sb, nullptr, scr_b, scr_bytes, lt_t, lt_t ? fl_t : 0u))) break;
+                KASF_MARK();
+            } while (0);
+            if (forked) {
+                // join -- also after a launch error, so that the caller's stream (or capture) is never left with
+                // un-joined side-stream work
+                bool ok = cudaEventRecord(ctx->e[1], sg) == cudaSuccess && cudaEventRecord(ctx->e[2], sb) == cudaSuccess &&
+                          cudaStreamWaitEvent(st, ctx->e[1], 0) == cudaSuccess && cudaStreamWaitEvent(st, ctx->e[2], 0) == cudaSuccess;
+                forked = false;
+                if (!ok && !rc) rc = cuda_status() ? cuda_status() : KASF_EINVAL;
             }
+            if (rc) break;
             if ((rc = launch_fusion(blob, l, s.A, s.G, s.Bn, s.X, tokens, st))) break;
             KASF_MARK();
         }
@@ -313,28 +365,24 @@ static int forward_impl(const kasf_config* cfg, const void* packed_dev, const fl
         KASF_MARK();
     }
 #undef KASF_MARK
-    // (all side-stream work is ordered before the caller's stream by the joins.  Under stream capture the fork / join
-    //  becomes part of the captured graph and the two streams and three events are left alive with it: a few hundred
-    //  bytes per captured graph, never per replay)
-    if (!capturing) {
-        for (int i = 0; i < 3; ++i)
-            if (side_e[i]) cudaEventDestroy(side_e[i]);
-        for (int i = 0; i < 2; ++i)
-            if (side_s[i]) cudaStreamDestroy(side_s[i]);
-    }
     return rc;
 }
 
 int kasf_forward(const kasf_config* cfg, const void* packed_dev, const float* x_dev, float* y_dev, float* rep_dev,
                  int B, void* ws_dev, size_t ws_bytes, void* stream) {
-    return forward_impl(cfg, packed_dev, x_dev, y_dev, rep_dev, B, ws_dev, ws_bytes, stream, nullptr);
+    return forward_impl(cfg, packed_dev, x_dev, y_dev, rep_dev, B, ws_dev, ws_bytes, stream, nullptr, nullptr);
+}
+
+int kasf_forward_ex(const kasf_config* cfg, const void* packed_dev, const float* x_dev, float* y_dev, float* rep_dev,
+                    int B, void* ws_dev, size_t ws_bytes, void* stream, const kasf_forward_opts* opts) {
+    return forward_impl(cfg, packed_dev, x_dev, y_dev, rep_dev, B, ws_dev, ws_bytes, stream, nullptr, opts);
 }
 
 int kasf_forward_timed(const kasf_config* cfg, const void* packed_dev, const float* x_dev, float* y_dev,
                        float* rep_dev, int B, void* ws_dev, size_t ws_bytes, void* stream, void** events,
                        int n_events) {
     if (!events || n_events < kasf_forward_marks(cfg, B) + 1) return KASF_EINVAL;
-    return forward_impl(cfg, packed_dev, x_dev, y_dev, rep_dev, B, ws_dev, ws_bytes, stream, events);
+    return forward_impl(cfg, packed_dev, x_dev, y_dev, rep_dev, B, ws_dev, ws_bytes, stream, events, nullptr);
 }
 
 void* kasf_event_create(void) {

@@ -1,0 +1,379 @@
+// kasf_exact.cu -- KASF_PRECISION_EXACT: the forward pass in the reference's own arithmetic.
+//
+// The fast path rounds the operands of every projection to bf16 (2^-9) and the MLP hidden activation to fp16, which a
+// trained checkpoint (layer scales ~0.1) turns into ~0.5 mm of output difference against the fp32 reference -- fifty
+// times the 1e-2 mm bar of BASELINE.json.  This path is the accuracy yardstick: fp32 FMA on CUDA cores for every
+// contraction (no tensor cores, no reduced-precision operand anywhere), erf GELU (model/modules/mlp.py:24-30), expf
+// softmax, the similarity / top-k in plain fp32 like graph.py:108-111, straight from the fp32 weight image.  It is
+// unfused -- one kernel per LayerNorm / projection / mixer core, activations in a caller-provided workspace -- and an
+// order of magnitude slower than the fast path; it exists so that `precision="exact"` reproduces the reference to
+// fp32 summation-order noise (tests/test_gpu_forward.py: <= 1e-2 mm on the stress goldens).
+//
+// Features, fusion and head are the fast path's own kernels: they are fp32 FMA kernels already (kasf_features.cu,
+// kasf_head.cu; <= 1e-5 / 2e-6 against the oracle), so the packed blob is needed next to the image.
+//
+//   FormerModule (KASportsFormer.py:103-118)   z = LN1(v); v += ls1 * MIX(z [, LN_limb(XL)]); v += ls2 * fc2(gelu(fc1(LN2(v))))
+//   Attention (selfattention.py:44-60)         qkv = z Wqkv^T; per (group, head) softmax(q k^T / 4) v; proj
+//   BoneCrossAttention (bone_crossattention.py:43-62)   q = z Wq^T, kv = zl Wkv^T
+//   GCN (graph.py:99-134)                      relu(z + BN_node(A_hat (z V^T + bV) + z U^T + bU))
+#include <cstring>
+#include <vector>
+
+#include "kasf_internal.h"
+
+namespace kasf {
+namespace {
+
+// ------------------------------------------------------------------ LayerNorm: warp per row, two-pass fp32
+__global__ void __launch_bounds__(256) ex_ln_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                    const float* __restrict__ b, float* __restrict__ z, long long rows) {
+    const int lane = threadIdx.x & 31;
+    const long long r0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, step = ((long long)gridDim.x * blockDim.x) >> 5;
+    // (tensors of the weight image start at arbitrary float offsets -- the limb MLPs have 1-element biases -- so
+    //  nothing read from it is vectorised)
+    const float4 gam = make_float4(g[lane * 4], g[lane * 4 + 1], g[lane * 4 + 2], g[lane * 4 + 3]);
+    const float4 bet = make_float4(b[lane * 4], b[lane * 4 + 1], b[lane * 4 + 2], b[lane * 4 + 3]);
+    for (long long r = r0; r < rows; r += step) {
+        const float4 v = *reinterpret_cast<const float4*>(x + r * D + lane * 4);
+        float s = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s * (1.0f / D);
+        const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+        float q = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = 1.0f / sqrtf(q * (1.0f / D) + 1e-5f);
+        float4 o4;
+        o4.x = d0 * rstd * gam.x + bet.x, o4.y = d1 * rstd * gam.y + bet.y;
+        o4.z = d2 * rstd * gam.z + bet.z, o4.w = d3 * rstd * gam.w + bet.w;
+        *reinterpret_cast<float4*>(z + r * D + lane * 4) = o4;
+    }
+}
+
+// ------------------------------------------------------------------ C[M,N] = A[M,K] W[N,K]^T (+ bias), fp32 FMA
+// 64 x 64 output tile, K in steps of 16 through shared memory, 256 threads x (4 x 4) outputs, k summed in order.
+// EPI 0: C = acc + bias | 1: C = gelu_erf(acc + bias) | 2: C = R + ls * (acc + bias)   (bias may be null)
+template <int EPI>
+__global__ void __launch_bounds__(256) ex_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W,
+                                                      const float* __restrict__ bias, float* C, int ldc,
+                                                      long long M, int N, int K, const float* R,      // (R may alias C)
+                                                      const float* __restrict__ ls) {
+    __shared__ float As[16][64 + 4], Ws[16][64 + 4];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const long long m0 = (long long)blockIdx.x * 64;
+    const int n0 = blockIdx.y * 64;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int lr = threadIdx.x >> 2, lk = (threadIdx.x & 3) * 4;     // loader: row 0..63, k 0,4,8,12
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), w = a;
+        if (m0 + lr < M) a = *reinterpret_cast<const float4*>(A + (m0 + lr) * lda + k0 + lk);
+        if (n0 + lr < N) {
+            const float* wp = W + (size_t)(n0 + lr) * K + k0 + lk;
+            w = make_float4(wp[0], wp[1], wp[2], wp[3]);
+        }
+        As[lk][lr] = a.x, As[lk + 1][lr] = a.y, As[lk + 2][lr] = a.z, As[lk + 3][lr] = a.w;
+        Ws[lk][lr] = w.x, Ws[lk + 1][lr] = w.y, Ws[lk + 2][lr] = w.z, Ws[lk + 3][lr] = w.w;
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 wv = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
+            const float ar[4] = {av.x, av.y, av.z, av.w}, wr[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], wr[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            float v = acc[i][j] + (bias ? bias[n] : 0.f);
+            if (EPI == 1) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+            if (EPI == 2) v = R[m * ldc + n] + ls[n] * v;
+            C[m * ldc + n] = v;
+        }
+    }
+}
+
+template <int EPI>
+int ex_gemm(const float* A, int lda, const float* W, const float* bias, float* C, int ldc, long long M, int N, int K,
+            const float* R, const float* ls, cudaStream_t st) {
+    dim3 grid((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64));
+    ex_gemm_kernel<EPI><<<grid, 256, 0, st>>>(A, lda, W, bias, C, ldc, M, N, K, R, ls);
+    return cuda_status();
+}
+
+// ------------------------------------------------------------------ attention core, fp32
+// One CTA per (group, head): q, k, v [n x 16] in shared memory; thread = query row; two passes over the keys
+// (row maximum, then exp / sum / weighted values), softmax(q k^T * 16^-1/2) v like selfattention.py:18-41.
+// Group g: spatial (b, t) -> tokens g*17 + j; temporal (b, j) -> tokens (b*T + t)*17 + j.
+__global__ void __launch_bounds__(128) ex_attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k,
+                                                           const float* __restrict__ v, int ldkv, float* __restrict__ o,
+                                                           int T, int temporal) {
+    extern __shared__ float sm[];
+    const int n = temporal ? T : J, h = blockIdx.y;
+    const long long g = blockIdx.x;
+    float *sq = sm, *sk = sm + n * DH, *sv = sm + 2 * n * DH;
+    auto token = [&](int i) -> long long {
+        if (!temporal) return g * J + i;
+        const long long b = g / J;
+        return (b * T + i) * J + g % J;
+    };
+    for (int idx = threadIdx.x; idx < n * DH; idx += blockDim.x) {
+        const int i = idx / DH, c = idx % DH;
+        const long long t = token(i);
+        sq[idx] = q[t * ldq + h * DH + c];
+        sk[idx] = k[t * ldkv + h * DH + c];
+        sv[idx] = v[t * ldkv + h * DH + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float qi[DH];
+#pragma unroll
+        for (int c = 0; c < DH; ++c) qi[c] = sq[i * DH + c];
+        float mx = -INFINITY;
+        for (int j = 0; j < n; ++j) {
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < DH; ++c) s = fmaf(qi[c], sk[j * DH + c], s);
+            mx = fmaxf(mx, s * 0.25f);
+        }
+        float l = 0.f, acc[DH];
+#pragma unroll
+        for (int c = 0; c < DH; ++c) acc[c] = 0.f;
+        for (int j = 0; j < n; ++j) {
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < DH; ++c) s = fmaf(qi[c], sk[j * DH + c], s);
+            const float p = expf(s * 0.25f - mx);
+            l += p;
+#pragma unroll
+            for (int c = 0; c < DH; ++c) acc[c] = fmaf(p, sv[j * DH + c], acc[c]);
+        }
+        const float inv = 1.0f / l;
+        const long long t = token(i);
+#pragma unroll
+        for (int c = 0; c < DH; ++c) o[t * D + h * DH + c] = acc[c] * inv;
+    }
+}
+
+// ------------------------------------------------------------------ GCN aggregation, fp32
+// agg_i = sum_j A_ij / sqrt(d_i d_j) * P_j with row-sum degrees (graph.py:77-90, 126).
+// Spatial: the fixed skeleton adjacency; warp per token.
+__constant__ int ex_nbr[68] = KASF_NBR;
+__constant__ int ex_deg[17] = KASF_DEG;
+__global__ void __launch_bounds__(256) ex_gcn_spatial_kernel(const float* __restrict__ P, float* __restrict__ agg, long long tokens) {
+    const int lane = threadIdx.x & 31;
+    const long long w0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, step = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long t = w0; t < tokens; t += step) {
+        const int j = (int)(t % J);
+        const long long base = t - j;
+        const float di = 1.0f / sqrtf((float)ex_deg[j]);
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int n = 0; n < 4; ++n) {
+            const int nb = ex_nbr[j * 4 + n];
+            if (nb < 0) break;
+            const float cf = di * (1.0f / sqrtf((float)ex_deg[nb]));
+            const float4 pv = *reinterpret_cast<const float4*>(P + (base + nb) * D + lane * 4);
+            a.x = fmaf(cf, pv.x, a.x), a.y = fmaf(cf, pv.y, a.y), a.z = fmaf(cf, pv.z, a.z), a.w = fmaf(cf, pv.w, a.w);
+        }
+        *reinterpret_cast<float4*>(agg + t * D + lane * 4) = a;
+    }
+}
+
+// Temporal: one CTA per (clip, joint) sequence.  S = z z^T in fp32 (graph.py:108), threshold = 4th largest of the row
+// with multiplicity (topk, :109), A = S >= thr (:111), degrees = row sums; then the aggregation of P.
+__global__ void __launch_bounds__(256) ex_gcn_temporal_kernel(const float* __restrict__ z, const float* __restrict__ P,
+                                                              float* __restrict__ agg, int T) {
+    extern __shared__ float sm[];
+    float* sz = sm;                                            // [T][128 + 1]
+    uint32_t* adj = reinterpret_cast<uint32_t*>(sm + T * (D + 1));   // [T][8]
+    float* rsd = reinterpret_cast<float*>(adj + T * 8);        // [T]
+    const long long seq = blockIdx.x, b = seq / J;
+    const int j = (int)(seq % J);
+    auto token = [&](int t) -> long long { return (b * T + t) * J + j; };
+    for (int idx = threadIdx.x; idx < T * D; idx += blockDim.x) {
+        const int t = idx / D, c = idx % D;
+        sz[t * (D + 1) + c] = z[token(t) * D + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < T; i += blockDim.x) {
+        float top[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        for (int jj = 0; jj < T; ++jj) {
+            float s = 0.f;
+            for (int c = 0; c < D; ++c) s = fmaf(sz[i * (D + 1) + c], sz[jj * (D + 1) + c], s);
+            if (s > top[3]) {
+                top[3] = s;
+#pragma unroll
+                for (int q = 3; q > 0; --q)
+                    if (top[q] > top[q - 1]) {
+                        const float tmp = top[q];
+                        top[q] = top[q - 1], top[q - 1] = tmp;
+                    }
+            }
+        }
+        const float thr = top[3];
+        int deg = 0;
+        for (int w = 0; w < 8; ++w) adj[i * 8 + w] = 0u;
+        for (int jj = 0; jj < T; ++jj) {
+            float s = 0.f;
+            for (int c = 0; c < D; ++c) s = fmaf(sz[i * (D + 1) + c], sz[jj * (D + 1) + c], s);
+            if (s >= thr) adj[i * 8 + (jj >> 5)] |= 1u << (jj & 31), ++deg;
+        }
+        rsd[i] = 1.0f / sqrtf((float)deg);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = warp; i < T; i += 8) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float di = rsd[i];
+        for (int w = 0; w < 8; ++w) {
+            uint32_t bits = adj[i * 8 + w];
+            while (bits) {
+                const int jj = 32 * w + __ffs(bits) - 1;
+                bits &= bits - 1;
+                const float cf = di * rsd[jj];
+                const float4 pv = *reinterpret_cast<const float4*>(P + token(jj) * D + lane * 4);
+                a.x = fmaf(cf, pv.x, a.x), a.y = fmaf(cf, pv.y, a.y), a.z = fmaf(cf, pv.z, a.z), a.w = fmaf(cf, pv.w, a.w);
+            }
+        }
+        *reinterpret_cast<float4*>(agg + token(i) * D + lane * 4) = a;
+    }
+}
+
+// out = x + ls1 * relu(z + BN_node(agg + qu)), BatchNorm1d over the node axis in eval mode (graph.py:37, 129)
+__global__ void __launch_bounds__(256) ex_gcn_epilogue_kernel(const float* x /* may alias out */, const float* __restrict__ z,
+                                                              const float* __restrict__ agg, const float* __restrict__ qu,
+                                                              const float* __restrict__ ls, const float* __restrict__ bnw,
+                                                              const float* __restrict__ bnb, const float* __restrict__ bnm,
+                                                              const float* __restrict__ bnv, float* out,
+                                                              long long tokens, int T, int temporal) {
+    const long long n = tokens * D;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long t = i / D;
+        const int c = (int)(i % D);
+        const int node = temporal ? (int)((t / J) % T) : (int)(t % J);
+        const float bn = (agg[i] + qu[i] - bnm[node]) / sqrtf(bnv[node] + 1e-5f) * bnw[node] + bnb[node];
+        out[i] = x[i] + ls[c] * fmaxf(z[i] + bn, 0.f);
+    }
+}
+
+struct ExBuf {
+    float *X, *XB, *XL, *A, *G, *Bn, *Z, *ZL, *QKV, *H, *T1, *T2;
+};
+constexpr int EX_UNITS = 6 + 1 + 1 + 3 + 4 + 1 + 1;      // [tokens x 128] float blocks
+
+long long ex_chunk(const kasf_config* cfg, int B) {
+    const long long per_clip = (long long)cfg->n_frames * J * D * 4 * EX_UNITS;
+    long long c = (2LL << 30) / per_clip;
+    if (c < 1) c = 1;
+    return c < B ? c : B;
+}
+
+}  // namespace
+
+size_t exact_workspace_bytes(const kasf_config* cfg, int B) {
+    const long long tokens = ex_chunk(cfg, B) * cfg->n_frames * J;
+    return (size_t)EX_UNITS * (((size_t)tokens * D * 4 + 1023) / 1024 * 1024);
+}
+
+int exact_forward(const kasf_config* cfg, const float* image, const uint8_t* blob, const float* x_dev, float* y_dev,
+                  float* rep_dev, int B, void* ws, size_t ws_bytes, cudaStream_t st) {
+    (void)ws_bytes;
+    GlobalImg Gi;
+    std::vector<LayerImg> L((size_t)cfg->n_layers);
+    walk_image(cfg, &Gi, L.data(), [](const char*, size_t, size_t) {});
+    const int T = cfg->n_frames;
+    const long long chunk = ex_chunk(cfg, B);
+    const size_t unit = ((size_t)chunk * T * J * D * 4 + 1023) / 1024 * 1024;
+    uint8_t* p = static_cast<uint8_t*>(ws);
+    ExBuf w;
+    w.X = (float*)p, w.XB = (float*)(p + unit), w.XL = (float*)(p + 2 * unit), w.A = (float*)(p + 3 * unit);
+    w.G = (float*)(p + 4 * unit), w.Bn = (float*)(p + 5 * unit), w.Z = (float*)(p + 6 * unit), w.ZL = (float*)(p + 7 * unit);
+    w.QKV = (float*)(p + 8 * unit), w.H = (float*)(p + 11 * unit), w.T1 = (float*)(p + 15 * unit), w.T2 = (float*)(p + 16 * unit);
+    const int sms = sm_count();
+    int rc = KASF_OK;
+#define EX(call) do { if ((rc = (call))) return rc; } while (0)
+    for (long long b0 = 0; b0 < B; b0 += chunk) {
+        const int nb = (int)(B - b0 < chunk ? B - b0 : chunk);
+        const long long M = (long long)nb * T * J;
+        const int ew_grid = (int)(((M * D + 255) / 256) < (long long)sms * 16 ? ((M * D + 255) / 256) : (long long)sms * 16);
+        const int ln_grid = (int)(((M + 7) / 8) < (long long)sms * 16 ? ((M + 7) / 8) : (long long)sms * 16);
+        EX(launch_features(blob, x_dev + (size_t)b0 * T * J * 3, nullptr, nullptr, w.X, w.XB, w.XL, (long long)nb * T, st));
+        auto ln = [&](const float* in, size_t g, size_t b, float* out) {
+            ex_ln_kernel<<<ln_grid, 256, 0, st>>>(in, image + g, image + b, out, M);
+            return cuda_status();
+        };
+        // one FormerModule: in -> out (may alias)
+        auto module = [&](const ModuleImg& m, int kind, int temporal, const float* in, float* out) -> int {
+            int r;
+            if ((r = ln(in, m.n1w, m.n1b, w.Z))) return r;
+            if (kind == KASF_KIND_GRAPH) {
+                // P = z V^T + bV, agg = A_hat P, qu = z U^T + bU, out = in + ls1 * relu(z + BN(agg + qu))
+                if ((r = ex_gemm<0>(w.Z, D, image + m.Vw, image + m.Vb, w.T1, D, M, D, D, nullptr, nullptr, st))) return r;
+                if (temporal) {
+                    const size_t smem = ((size_t)T * (D + 1) + (size_t)T * 8 + T) * 4;
+                    cudaFuncSetAttribute(ex_gcn_temporal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    ex_gcn_temporal_kernel<<<nb * J, 256, smem, st>>>(w.Z, w.T1, w.T2, T);
+                } else {
+                    ex_gcn_spatial_kernel<<<ln_grid, 256, 0, st>>>(w.T1, w.T2, M);
+                }
+                if ((r = cuda_status())) return r;
+                if ((r = ex_gemm<0>(w.Z, D, image + m.Uw, image + m.Ub, w.T1, D, M, D, D, nullptr, nullptr, st))) return r;
+                ex_gcn_epilogue_kernel<<<ew_grid, 256, 0, st>>>(in, w.Z, w.T2, w.T1, image + m.ls1, image + m.bnw, image + m.bnb,
+                                                               image + m.bnm, image + m.bnv, out, M, T, temporal);
+                if ((r = cuda_status())) return r;
+            } else {
+                const float *q, *k, *v;
+                int ldq, ldkv;
+                if (kind == KASF_KIND_ATTENTION) {
+                    if ((r = ex_gemm<0>(w.Z, D, image + m.qkvw, nullptr, w.QKV, 3 * D, M, 3 * D, D, nullptr, nullptr, st))) return r;
+                    q = w.QKV, k = w.QKV + D, v = w.QKV + 2 * D, ldq = ldkv = 3 * D;
+                } else {
+                    if ((r = ln(w.XL, m.nlw, m.nlb, w.ZL))) return r;
+                    if ((r = ex_gemm<0>(w.Z, D, image + m.qw, nullptr, w.T1, D, M, D, D, nullptr, nullptr, st))) return r;
+                    if ((r = ex_gemm<0>(w.ZL, D, image + m.kvw, nullptr, w.QKV, 2 * D, M, 2 * D, D, nullptr, nullptr, st))) return r;
+                    q = w.T1, k = w.QKV, v = w.QKV + D, ldq = D, ldkv = 2 * D;
+                }
+                const int n = temporal ? T : J;
+                const long long groups = temporal ? (long long)nb * J : (long long)nb * T;
+                ex_attention_kernel<<<dim3((unsigned)groups, HEADS), 128, (size_t)3 * n * DH * 4, st>>>(q, ldq, k, v, ldkv, w.T2, T, temporal);
+                if ((r = cuda_status())) return r;
+                // out = in + ls1 * (o Wproj^T + bproj)
+                if ((r = ex_gemm<2>(w.T2, D, image + m.projw, image + m.projb, out, D, M, D, D, in, image + m.ls1, st))) return r;
+            }
+            // out += ls2 * fc2(gelu(fc1(LN2(out))))
+            if ((r = ln(out, m.n2w, m.n2b, w.Z))) return r;
+            if ((r = ex_gemm<1>(w.Z, D, image + m.fc1w, image + m.fc1b, w.H, HID, M, HID, D, nullptr, nullptr, st))) return r;
+            return ex_gemm<2>(w.H, HID, image + m.fc2w, image + m.fc2b, out, D, M, D, HID, out, image + m.ls2, st);
+        };
+        for (int l = 0; l < cfg->n_layers; ++l) {
+            const LayerImg& li = L[(size_t)l];
+            EX(module(li.m[0], KASF_KIND_ATTENTION, 0, w.X, w.A));
+            EX(module(li.m[1], KASF_KIND_ATTENTION, 1, w.A, w.A));
+            EX(module(li.m[2], KASF_KIND_GRAPH, 0, w.X, w.G));
+            EX(module(li.m[3], KASF_KIND_GRAPH, 1, w.G, w.G));
+            EX(module(li.m[4], KASF_KIND_BONE, 0, l == 0 ? w.XB : w.X, w.Bn));
+            EX(module(li.m[5], KASF_KIND_BONE, 1, w.Bn, w.Bn));
+            EX(launch_fusion(blob, l, w.A, w.G, w.Bn, w.X, M, st));
+        }
+        EX(launch_head(blob, w.X, y_dev ? y_dev + (size_t)b0 * T * J * 3 : nullptr,
+                       rep_dev ? rep_dev + (size_t)b0 * T * J * REP : nullptr, M, st));
+    }
+#undef EX
+    return rc;
+}
+
+}  // namespace kasf

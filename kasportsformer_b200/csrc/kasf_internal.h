@@ -33,7 +33,8 @@ int launch_fusion(const uint8_t* blob, int layer, const float* a, const float* g
 // `scratch` (module_scratch_bytes(B, T) bytes, 256-byte aligned) is needed by temporal modules with T > 128 only
 int launch_former_module(const uint8_t* blob, int layer, int kind, int mode, const float* in, const float* XL,
                          float* out, int B, int T, cudaStream_t st, unsigned long long* prof = nullptr,
-                         void* scratch = nullptr, size_t scratch_bytes = 0, const void* limb_tiles = nullptr);
+                         void* scratch = nullptr, size_t scratch_bytes = 0, const void* limb_tiles = nullptr,
+                         unsigned flags = 0);
 // Pre-normalised limb rows as bf16 operand tiles in the tile order of `mode` (0 bytes for temporal, T > 128): the
 // optional `limb_tiles` argument of a bone module of the same mode.
 size_t limb_tiles_bytes(int B, int T, int mode);
@@ -42,6 +43,10 @@ size_t module_scratch_bytes(int B, int T);
 int launch_metrics(int T, const float* pred, const float* pred_flip, const float* gt, const float* res,
                    const float* factor, const int32_t* action, int n_actions, double* sums, double* per_frame,
                    int B, cudaStream_t st);
+// KASF_PRECISION_EXACT (kasf_exact.cu): the reference's fp32 arithmetic on CUDA cores, from the fp32 weight image
+size_t exact_workspace_bytes(const kasf_config* cfg, int B);
+int exact_forward(const kasf_config* cfg, const float* image, const uint8_t* blob, const float* x, float* y, float* rep,
+                  int B, void* ws, size_t ws_bytes, cudaStream_t st);
 double host_p_mpjpe(const double* p, const double* g);
 int launch_flip(const float* in, float* out, long long frames, cudaStream_t st);
 int launch_test_gemm(const float* a, const float* w, float* d, int M, int N, cudaStream_t st);

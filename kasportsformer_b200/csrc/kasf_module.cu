@@ -1839,7 +1839,7 @@ int launch_limb_tiles(const float* XL, void* tiles, int B, int T, int mode, cuda
 
 int launch_former_module(const uint8_t* blob, int layer, int kind, int mode, const float* in, const float* XL,
                          float* out, int B, int T, cudaStream_t st, unsigned long long* prof, void* scratch,
-                         size_t scratch_bytes, const void* limb_tiles) {
+                         size_t scratch_bytes, const void* limb_tiles, unsigned flags) {
     if (B <= 0) return KASF_OK;
     if (kind < 0 || kind > 2 || mode < 0 || mode > 1) return KASF_EINVAL;
     if (kind == KASF_KIND_BONE && !XL) return KASF_EINVAL;
@@ -1858,7 +1858,8 @@ int launch_former_module(const uint8_t* blob, int layer, int kind, int mode, con
     p.srow = nullptr;
     p.xlt = kind == KASF_KIND_BONE ? static_cast<const uint8_t*>(limb_tiles) : nullptr;
     if (((uintptr_t)p.xlt & 127) != 0) return KASF_EINVAL;
-    if (mode == KASF_MODE_TEMPORAL && T > 128) return launch_long(p, kind, scratch, scratch_bytes, st);
+    if (mode == KASF_MODE_TEMPORAL && T > 128)
+        return (flags & KASF_FLAG_TWO_TILES) ? KASF_ESHAPE : launch_long(p, kind, scratch, scratch_bytes, st);
     int tc = 0;
     if (mode == KASF_MODE_SPATIAL) {
         p.groups_per_tile = 7;
@@ -1868,10 +1869,11 @@ int launch_former_module(const uint8_t* blob, int layer, int kind, int mode, con
         p.ntiles = (int)(((long long)B * J + p.groups_per_tile - 1) / p.groups_per_tile);
         tc = T <= 32 ? 0 : (T <= 64 ? 1 : 2);
     }
-    // two tiles in flight per SM (kasf_module_v2.cuh): short groups, bone modules fed from limb tiles.
-    // KASF_ONE_TILE=1 selects the one-tile kernel everywhere (A/B measurements, the stage tests cover both)
-    static const bool one_tile = [] { const char* e = getenv("KASF_ONE_TILE"); return e && e[0] == '1'; }();
-    if (tc == 0 && !one_tile && (kind != KASF_KIND_BONE || p.xlt)) {
+    // Two tiles in flight per SM (kasf_module_v2.cuh) -- opt-in (KASF_FLAG_TWO_TILES): parity-green, but measured SLOWER
+    // than this file's one-tile kernel on B200 (10.4k vs 13.3k clips/s at B = 1024, T = 27; DESIGN.md section 3 has the
+    // phase cycles, the event trace and the ncu counters that explain why).  The stage tests cover both kernels.
+    if (flags & KASF_FLAG_TWO_TILES) {
+        if (tc != 0 || (kind == KASF_KIND_BONE && !p.xlt)) return KASF_ESHAPE;
         const int sms = sm_count();
 #define KASF_CASE2(K, M) \
     if (kind == K && mode == M) return v2::launch_v2<K, M>(p, st, sms);

@@ -7,23 +7,25 @@
 // has been added to the residual rows and pipelines the two halves over consecutive tiles:
 //
 //   mixer group (8 warps, 128 registers)   tile i+1: row gather, LN1, Q|K|V drains, attention core / adjacency +
-//                                          aggregation, x1 = x + ls1 * mixer -> tensor memory
-//   MLP group   (8 warps,  96 registers)   tile i  : LN2, eight GELU epilogues (64 hidden columns each), output
-//                                          epilogue out = x1 + ls2 * (fc2 + b2) -> global memory
-//   weight producer (1 lane), MMA issuer (1 lane): one static, dependency-ordered sequence of 16 KB weight pieces and
-//                                          tcgen05.mma groups that interleaves the mixer projections of tile i+1 with
-//                                          the fc1 / fc2 pieces of tile i, through ONE 5-slot ring
+//                                          aggregation, x1 = x + ls1 * mixer -> the output rows in global memory (L2)
+//   MLP group   (8 warps,  96 registers)   tile i  : LN2(x1), eight GELU epilogues (64 hidden columns each), output
+//                                          epilogue out = x1 + ls2 * (fc2 + b2)
+//   service warpgroup (the CTA's first four warps): a weight producer and an MMA issuer PER GROUP.  The two streams
+//                                          (mixer projections of tile i+1; fc1 / fc2 pieces of tile i) never wait
+//                                          for each other; each has its own ring of 16 KB weight pieces.
 //
 // so that one tile's MMAs run under the other tile's CUDA-core phases and four warps per scheduler hide each other's
-// latencies.  What had to shrink to make two tiles fit (all measured on B200, scripts/micro/ts_mma.cu):
-//   tensor memory (512 columns): mixer accumulator 128 (K, V, Q, projection in turn) | fc1 accumulator 64 | the GELU
-//       output as the fc2 A OPERAND IN TENSOR MEMORY, 2 x 32 columns of packed fp16 pairs (tcgen05.mma with A from
-//       TMEM: no shared-memory tile, no swizzled stores, and the MMA reads only B from shared memory) | fc2
-//       accumulator 128 | x1 rows 128.  The residual rows x of the mixer tile are NOT kept on chip: the epilogue
-//       re-reads them (L2 hits, requested before the projection wait).
-//   shared memory (227 KB): A1 32 | K|V / staged rows / z 64 | A2 (LN2 output) 32 | ring 5 x 16 | vectors | small arrays.
-//       Weight pieces are 16 KB: a K-half [128 n x 64 k] of a chunk for the mixer projections and fc2, an N-half
-//       [64 n x 128 k] for fc1 -- both are contiguous blocks of the packed chunk images, so the blob is unchanged.
+// latencies.  Every MMA has N = 64 .. 128 and its accumulators are double-buffered, so that a group drains one
+// accumulator while the tensor cores fill the other (a hand-over per accumulator costs ~1-2k cycles next to sixteen busy
+// warps: measured, scripts/trace_v2.py).  What had to shrink to make two tiles fit (measured: scripts/micro/ts_mma.cu):
+//   tensor memory (512 columns): mixer accumulators 2 x 64 (the N-halves of K, V, Q, projection in turn) | fc1
+//       accumulators 2 x 64 | the GELU output as the fc2 A OPERAND IN TENSOR MEMORY, 2 x 32 columns of packed fp16 pairs
+//       (tcgen05.mma with A from TMEM: no shared-memory tile, no swizzled stores, the MMA reads only B from shared
+//       memory) | fc2 accumulator 128.  No residual rows live in tensor memory: the mixer epilogue re-reads x and
+//       hands x1 to the MLP group through the output rows themselves (L2 hits).
+//   shared memory (227 KB): A1 32 | K|V / staged rows / z 64 | A2 (LN2 output) 32 | rings 2 + 3 x 16 | vectors | small arrays.
+//       Weight pieces are 16 KB: an N-half [64 n x 128 k] of a chunk (two contiguous 8 KB blocks of the packed image)
+//       for the mixer projections and fc1, a K-half [128 n x 64 k] for fc2 -- the blob is unchanged.
 //   registers (640 threads x 96 at launch): the service warpgroup gives 64 of its 96 to the mixer group.
 //
 // Same arithmetic as the one-tile kernel (bf16 operands, fp16 hidden tile, fp32 everything else); the stage tests
@@ -32,9 +34,7 @@
 namespace v2 {
 
 constexpr int THREADS = 640;
-// Warp roles.  The service warps are the FIRST warpgroup of the CTA: a warp scheduler that prefers older warps then
-// serves the producers and MMA issuers -- a handful of instructions on the critical path of both groups -- ahead of
-// the sixteen compute warps instead of behind them.
+// Warp roles.  The service warps are the FIRST warpgroup of the CTA (setmaxnreg works on aligned groups of four warps).
 constexpr int W_PRODUCER_M = 0, W_MMA_M = 1, W_PRODUCER_P = 2, W_MMA_P = 3;
 constexpr int W_G0 = 4, W_G1 = 12;      // first warp of the mixer group / of the MLP group (8 warps each)
 constexpr int NSLOT = 5, MSLOTS = 2;    // ring slots: 0..MSLOTS-1 mixer projections, the rest fc1 / fc2 pieces
@@ -60,31 +60,32 @@ struct LayG1 {
     static constexpr int PAIR_BAR = 6;
 };
 
-constexpr uint32_t TM_ACC = 0, TM_H = 128, TM_HS0 = 192, TM_HS1 = 224, TM_OUT = 256, TM_XB = 384;
+// tensor memory columns: ACC0 | ACC1 mixer accumulators (64 each), H0 | H1 fc1 accumulators (64 each), HS0 | HS1 GELU
+// pieces (fp16 pairs, 32 each), OUT fc2 accumulator (128)
+constexpr uint32_t TM_ACC = 0, TM_H = 128, TM_HS = 256, TM_OUT = 384;
 
-// mbarriers.  Ring: FULL (bulk-copy bytes) / EMPTY (tcgen05.commit).
-//   mixer group -> issuer:  A1READY (A1 written: LN1 | attention output | A_hat z), ACCFREE (mixer accumulator drained)
-//   issuer -> mixer group:  ACCFULL
-//   mixer group -> MLP group: X1READY (x1 rows in tensor memory);  MLP group -> mixer group: XBFREE (output epilogue done)
-//   MLP group -> issuer:    A2READY (LN2 written), HFREE (fc1 accumulator drained), HSREADY0/1 (GELU piece in tensor memory)
-//   issuer -> MLP group:    HFULL, HSFREE0/1 (fc2 has read the piece), OUTFULL
+// mbarriers.  Rings: FULL (bulk-copy bytes) / EMPTY (tcgen05.commit).
+//   mixer group -> issuer:  A1READY (A1 written: LN1 | attention output | A_hat z), ACCFREE0/1 (accumulator drained)
+//   issuer -> mixer group:  ACCFULL0/1
+//   mixer group -> MLP group: X1READY (x1 rows stored);  MLP group -> mixer group: X1TAKEN (the MLP group has started that
+//                           tile: bounds the mixer group's lead, a waiter may lag one phase behind a barrier at most)
+//   MLP group -> issuer:    A2READY (LN2 written), HSREADY0/1 (GELU piece in tensor memory, its fc1 accumulator drained)
+//   issuer -> MLP group:    HFULL0/1, HSFREE0/1 (fc2 has read the piece), OUTFULL
 //   ROWS: the row gather of a tile has landed;  bone: LIMBFULL (limb operand tile landed in A1), A1FREE (projection done)
-enum { BB_FULL0 = 0, BB_EMPTY0 = NSLOT, BB_A1READY = 2 * NSLOT, BB_ACCFREE, BB_ACCFULL, BB_X1READY, BB_XBFREE, BB_A2READY,
-       BB_HFREE, BB_HFULL, BB_HSREADY0, BB_HSREADY1, BB_HSFREE0, BB_HSFREE1, BB_OUTFULL, BB_ROWS, BB_LIMBFULL, BB_A1FREE,
-       BB_COUNT };
+enum { BB_FULL0 = 0, BB_EMPTY0 = NSLOT, BB_A1READY = 2 * NSLOT, BB_ACCFREE0, BB_ACCFREE1, BB_ACCFULL0, BB_ACCFULL1, BB_X1READY,
+       BB_X1TAKEN, BB_A2READY, BB_HFREE0, BB_HFREE1, BB_HFULL0, BB_HFULL1, BB_HSREADY0, BB_HSREADY1, BB_HSFREE0, BB_HSFREE1,
+       BB_OUTFULL, BB_ROWS, BB_LIMBFULL, BB_A1FREE, BB_COUNT };
 static_assert(BB_COUNT <= 32 && BB_COUNT * 8 + 8 <= 512, "barrier block / one-register phase bits");
 
-// (tcgen05.mma with the A operand in tensor memory: 16-bit pairs, lane = row, 8 columns per K = 16)
 // The 64-bit shared-memory descriptor of a 128-byte-swizzled K-major operand differs between operands only in its low
 // word (the start address in 16-byte units, LBO in the upper half); the high word (SBO = 1024 B, version 1, SWIZZLE_128B)
-// is a constant that the MMA wrappers below splice in, so the issuer keeps 32-bit values only.
-constexpr uint32_t DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
-__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+// is a constant that the MMA wrappers below splice in, so the issuers keep 32-bit values only.
 // The issuer WARPS run their loops with all 32 lanes on warp-uniform values and hand each group of MMAs and its commits
 // to ONE lane chosen by elect.sync: ptxas then keeps descriptors and addresses in uniform registers and emits
 // back-to-back UTCHMMA (2-3 instructions per MMA).  Issued from inside an `if (lane == 0)` branch every MMA cost ~10
-// instructions -- R2UR moves and an ELECT "waterfall" loop, because ptxas cannot know that one lane is active -- which,
-// next to sixteen busy compute warps, made a group of eight MMAs take ~1.2k cycles to issue (trace of round 2).
+// instructions -- R2UR moves and an ELECT "waterfall" loop, because ptxas cannot know that one lane is active.
+constexpr uint32_t DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
 __device__ __forceinline__ void umma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
@@ -95,6 +96,7 @@ __device__ __forceinline__ void umma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t
         "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI)
         : "memory");
 }
+// A operand in tensor memory (16-bit pairs, lane = row, 8 columns per K = 16)
 __device__ __forceinline__ void umma_ts_lo(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
@@ -117,8 +119,16 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
+// 256-bit global accesses that bypass L1: x1 travels between the two groups through L2 (and a temporal module may work
+// in place: the rows a tile re-reads must never come out of a stale L1 line)
+__device__ __forceinline__ void ldcg256(const float* p, float* v) {
+    asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p)
+                 : "memory");
+}
 
-// chunk index (kasf_layout.h) of mixer op m
+// chunk index (kasf_layout.h) of mixer projection m
 template <int KIND>
 __device__ __forceinline__ int mixer_chunk(int m) {
     if (KIND == KASF_KIND_GRAPH) return m;                  // U, V
@@ -146,16 +156,6 @@ struct WaiterS {
         phases ^= 1u << idx;
     }
 };
-
-__device__ __forceinline__ void warp_arrive2(uint64_t* a, uint64_t* b, int lane) {
-    fence_proxy_async();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) {
-        mbar_arrive(a);
-        mbar_arrive(b);
-    }
-}
 
 // PROF builds: event trace of CTA 0, tiles 2..4: one region of TRACE_REGION events per role (0 mixer group thread 0,
 // 1 MLP group thread 0, 2 / 3 the issuers, 4 / 5 the producers), plain stores (an atomic counter would put an L2
@@ -191,8 +191,8 @@ __global__ void __launch_bounds__(THREADS, 1) former_module_v2_kernel(const ModP
     if (tid == 0) {
         if ((smem_u32(sm) & 1023u) != 0) __trap();
         for (int i = 0; i < BB_COUNT; ++i) {
-            const bool by_warps = i == BB_A1READY || i == BB_ACCFREE || i == BB_X1READY || i == BB_XBFREE || i == BB_A2READY ||
-                                  i == BB_HFREE || i == BB_HSREADY0 || i == BB_HSREADY1;
+            const bool by_warps = i == BB_A1READY || i == BB_ACCFREE0 || i == BB_ACCFREE1 || i == BB_X1READY || i == BB_X1TAKEN ||
+                                  i == BB_A2READY || i == BB_HFREE0 || i == BB_HFREE1 || i == BB_HSREADY0 || i == BB_HSREADY1;
             mbar_init(&bars[i], by_warps ? CW : (i == BB_ROWS ? CW * 32 * 2 : 1));
         }
         fence_mbar_init();
@@ -208,13 +208,13 @@ __global__ void __launch_bounds__(THREADS, 1) former_module_v2_kernel(const ModP
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const int n_local = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // >= 1: grid <= ntiles
+    constexpr int NM = KIND == KASF_KIND_GRAPH ? 2 : 4;      // mixer projections per tile, two N-halves each
 
     if (warp < W_G0) {
         // ===================== service warpgroup =====================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
-        constexpr int NM = KIND == KASF_KIND_GRAPH ? 2 : 4;      // mixer projections per tile
         if (warp == W_PRODUCER_M && lane == 0) {
-            // ---- mixer ring: the K-halves of the tile's projections, in order
+            // ---- mixer ring: the N-halves of the tile's projections, in order
             uint32_t slot = 0, ph = 0, ph_a1free = 0;
             Tracer<PROF> tr{4, 0, blockIdx.x == 0};
 #pragma unroll 1
@@ -225,45 +225,50 @@ __global__ void __launch_bounds__(THREADS, 1) former_module_v2_kernel(const ModP
                     const uint8_t* c = chunks + (size_t)mixer_chunk<KIND>(m) * CHUNK_BYTES;
 #pragma unroll 1
                     for (int h = 0; h < 2; ++h) {
+                        // rows 64 h .. + 63 of both K sub-tiles (two 8 KB blocks)
                         mbar_wait_suspend(&bars[BB_EMPTY0 + slot], ph ^ 1);
                         mbar_arrive_expect_tx(&bars[BB_FULL0 + slot], SLOT);
-                        bulk_g2s(sm + SM_RING + slot * SLOT, c + h * SLOT, SLOT, &bars[BB_FULL0 + slot]);
+                        uint8_t* dst = sm + SM_RING + slot * SLOT;
+                        bulk_g2s(dst, c + h * 8192, 8192, &bars[BB_FULL0 + slot]);
+                        bulk_g2s(dst + 8192, c + 16384 + h * 8192, 8192, &bars[BB_FULL0 + slot]);
                         tr.ev(p, 300 + m * 2 + h, k);
                         if (++slot == MSLOTS) slot = 0, ph ^= 1;
-                    }
-                    if (KIND == KASF_KIND_BONE && m == 0) {
-                        // the tile's normalised limb rows: one 32 KB bulk copy into A1 once the previous tile's
-                        // projection has read it (before V's pieces: those wait for K to be consumed, and K for this copy)
-                        if (k > 0) {
-                            mbar_wait_suspend(&bars[BB_A1FREE], ph_a1free);
-                            ph_a1free ^= 1;
+                        if (KIND == KASF_KIND_BONE && m == 0 && h == 1) {
+                            // the tile's normalised limb rows: one 32 KB bulk copy into A1 once the previous tile's
+                            // projection has read it (before V's pieces: those wait for K to be consumed, and K for this copy)
+                            if (k > 0) {
+                                mbar_wait_suspend(&bars[BB_A1FREE], ph_a1free);
+                                ph_a1free ^= 1;
+                            }
+                            mbar_arrive_expect_tx(&bars[BB_LIMBFULL], TILE_BYTES);
+                            bulk_g2s(sm + SM_A1, p.xlt + (size_t)tile * TILE_BYTES, TILE_BYTES, &bars[BB_LIMBFULL]);
                         }
-                        mbar_arrive_expect_tx(&bars[BB_LIMBFULL], TILE_BYTES);
-                        bulk_g2s(sm + SM_A1, p.xlt + (size_t)tile * TILE_BYTES, TILE_BYTES, &bars[BB_LIMBFULL]);
                     }
                 }
             }
             tr.done(p);
         } else if (warp == W_PRODUCER_P && lane == 0) {
-            // ---- MLP ring: fc1(0), then fc1(q+1), fc2(q) for q = 0..6, then fc2(7)
+            // ---- MLP ring: fc1(0), fc1(1), then fc2(q), fc1(q+2) for q = 0..7 (fc1 while q + 2 < 8)
             uint32_t slot = MSLOTS, ph = 0;
             Tracer<PROF> tr{5, 0, blockIdx.x == 0};
 #pragma unroll 1
             for (int k = 0; k < n_local; ++k) {
 #pragma unroll 1
-                for (int j = 0; j < 16; ++j) {
-                    const bool fc1 = j == 0 || ((j & 1) && j < 15);
-                    const int q = fc1 ? (j + 1) >> 1 : (j == 15 ? 7 : (j >> 1) - 1);
+                for (int j = 0; j < 18; ++j) {
+                    const int q = j < 2 ? j : (j - 2) >> 1;
+                    const bool fc1 = j < 2 || ((j - 2) & 1);
+                    const int piece = j < 2 ? j : (fc1 ? q + 2 : q);
+                    if (fc1 && piece >= 8) continue;
                     mbar_wait_suspend(&bars[BB_EMPTY0 + slot], ph ^ 1);
                     mbar_arrive_expect_tx(&bars[BB_FULL0 + slot], SLOT);
                     uint8_t* dst = sm + SM_RING + slot * SLOT;
                     if (fc1) {
-                        // an N-half of a W1 chunk: rows 64 (q & 1) .. + 63 of both K sub-tiles (two 8 KB blocks)
-                        const uint8_t* c = chunks + (size_t)(4 + (q >> 1)) * CHUNK_BYTES + (q & 1) * 8192;
+                        // an N-half of a W1 chunk: rows 64 (piece & 1) .. + 63 of both K sub-tiles (two 8 KB blocks)
+                        const uint8_t* c = chunks + (size_t)(4 + (piece >> 1)) * CHUNK_BYTES + (piece & 1) * 8192;
                         bulk_g2s(dst, c, 8192, &bars[BB_FULL0 + slot]);
                         bulk_g2s(dst + 8192, c + 16384, 8192, &bars[BB_FULL0 + slot]);
                     } else {
-                        bulk_g2s(dst, chunks + (size_t)(8 + (q >> 1)) * CHUNK_BYTES + (q & 1) * SLOT, SLOT, &bars[BB_FULL0 + slot]);
+                        bulk_g2s(dst, chunks + (size_t)(8 + (piece >> 1)) * CHUNK_BYTES + (piece & 1) * SLOT, SLOT, &bars[BB_FULL0 + slot]);
                     }
                     tr.ev(p, 320 + j, k);
                     if (++slot == NSLOT) slot = MSLOTS, ph ^= 1;
@@ -271,11 +276,11 @@ __global__ void __launch_bounds__(THREADS, 1) former_module_v2_kernel(const ModP
             }
             tr.done(p);
         } else if (warp == W_MMA_M) {
-            // ---- issuer of the mixer projections (tile the mixer group works on).  The two issuers are independent
-            //      threads with blocking waits: neither stream is ever held up behind the other group's progress, and
-            //      an MMA goes out as soon as its trigger fires (a polling loop over both streams reacted ~2k cycles late).
+            // ---- issuer of the mixer projections (tile the mixer group works on): N-half h of projection m goes to
+            //      accumulator h; it waits for that accumulator to be drained (ACCFREE h) and, where the A operand
+            //      changes, for A1
             const uint32_t a1_addr = smem_u32(sm + SM_A1), ring_addr = smem_u32(sm + SM_RING);
-            uint32_t phs = 0;                       // phase bit per barrier this thread waits on
+            uint32_t phs = (1u << BB_ACCFREE0) | (1u << BB_ACCFREE1);   // both accumulators start out free
             auto wait = [&](int idx) {           // lane 0 polls, the warp reconverges: the issue code stays warp-uniform
                 if (lane == 0) mbar_wait(&bars[idx], (phs >> idx) & 1u);
                 __syncwarp();
@@ -287,94 +292,91 @@ __global__ void __launch_bounds__(THREADS, 1) former_module_v2_kernel(const ModP
             for (int k = 0; k < n_local; ++k) {
 #pragma unroll 1
                 for (int m = 0; m < NM; ++m) {
-                    // A operand: A1READY (bone K: LIMBFULL); accumulator: ACCFREE
-                    uint32_t acc = 0;
-                    if (KIND == KASF_KIND_ATTENTION) {
-                        if (m == 0 || m == 3) wait(BB_A1READY);
-                        if ((m == 0 && k > 0) || m == 1 || m == 2) wait(BB_ACCFREE);
-                    } else if (KIND == KASF_KIND_BONE) {
-                        if (m == 0) wait(BB_LIMBFULL);
-                        if (m >= 2) wait(BB_A1READY);
-                        if ((m == 0 && k > 0) || m == 1) wait(BB_ACCFREE);
-                    } else {
-                        wait(BB_A1READY);
-                        if (m == 0 && k > 0) wait(BB_ACCFREE);
-                        if (m == 1) acc = 1;
-                    }
-                    tr.ev(p, 100 + m, k);
-                    // [128 x 128] x [128 x 128]^T as two K-halves of 4 K-steps
-                    const uint32_t idesc = umma_idesc_bf16(128, 128);
+                    bool new_a, accumulate = false;
+                    if (KIND == KASF_KIND_ATTENTION) new_a = m == 0 || m == 3;
+                    else if (KIND == KASF_KIND_BONE) new_a = m != 1;
+                    else new_a = true, accumulate = m == 1;
+                    if (new_a) wait((KIND == KASF_KIND_BONE && m == 0) ? BB_LIMBFULL : BB_A1READY);
+                    const uint32_t idesc = umma_idesc_bf16(128, 64);
+                    const uint32_t a_lo = desc_lo(a1_addr);
 #pragma unroll 1
                     for (uint32_t h = 0; h < 2; ++h) {
+                        if (!accumulate) wait(BB_ACCFREE0 + h);
                         if (lane == 0) mbar_wait(&bars[BB_FULL0 + mslot], mph);
                         __syncwarp();
                         tc_fence_after();
-                        const uint32_t b_lo = desc_lo(ring_addr + mslot * SLOT), a_lo = desc_lo(a1_addr + h * 16384u);
+                        tr.ev(p, 100 + m * 2 + h, k);
+                        const uint32_t b_lo = desc_lo(ring_addr + mslot * SLOT);
                         if (elect_one()) {
 #pragma unroll
-                            for (uint32_t kk = 0; kk < 4; ++kk) umma_lo(tmem + TM_ACC, a_lo + kk * 2u, b_lo + kk * 2u, idesc, (acc || kk) ? 1u : 0u);
+                            for (uint32_t ks = 0; ks < 8; ++ks)
+                                umma_lo(tmem + TM_ACC + h * 64, a_lo + (((ks >> 2) * 16384u + (ks & 3) * 32u) >> 4),
+                                        b_lo + (((ks >> 2) * 8192u + (ks & 3) * 32u) >> 4), idesc, (accumulate || ks > 0) ? 1u : 0u);
                             tc_commit(&bars[BB_EMPTY0 + mslot]);
-                            if (h) {
-                                tc_commit(&bars[BB_ACCFULL]);
-                                if (KIND == KASF_KIND_BONE && m == 3) tc_commit(&bars[BB_A1FREE]);
-                            }
+                            tc_commit(&bars[BB_ACCFULL0 + h]);
+                            if (KIND == KASF_KIND_BONE && m == 3 && h == 1) tc_commit(&bars[BB_A1FREE]);
                         }
                         __syncwarp();
-                        acc = 1;
                         if (++mslot == MSLOTS) mslot = 0, mph ^= 1;
                     }
-                    tr.ev(p, 110 + m, k);
                 }
             }
             tr.done(p);
         } else if (warp == W_MMA_P) {
-            // ---- issuer of the fc1 / fc2 pieces (tile the MLP group works on)
+            // ---- issuer of the fc1 / fc2 pieces (tile the MLP group works on).  fc1 runs two pieces ahead of the GELU
+            //      epilogues over the two accumulators; ONE trigger per piece (HSREADY q: the GELU piece is in tensor
+            //      memory and its fc1 accumulator drained) releases fc2(q) and fc1(q+2) together -- a barrier check
+            //      costs this warp ~100 cycles even when it has completed, sixteen of them per tile were its bottleneck
             const uint32_t a2_addr = smem_u32(sm + SM_A2), ring_addr = smem_u32(sm + SM_RING);
             uint32_t phs = 0;
-            auto wait = [&](int idx) {           // lane 0 polls, the warp reconverges: the issue code stays warp-uniform
+            auto wait = [&](int idx) {
                 if (lane == 0) mbar_wait(&bars[idx], (phs >> idx) & 1u);
                 __syncwarp();
                 phs ^= 1u << idx;
             };
             uint32_t pslot = MSLOTS, pph = 0;
-            bool first = true;
             Tracer<PROF> tr{3, 0, blockIdx.x == 0 && lane == 0};
+            auto slot_ready = [&]() -> uint32_t {
+                if (lane == 0) mbar_wait(&bars[BB_FULL0 + pslot], pph);
+                __syncwarp();
+                tc_fence_after();
+                return desc_lo(ring_addr + pslot * SLOT);
+            };
+            auto slot_next = [&]() {
+                if (++pslot == NSLOT) pslot = MSLOTS, pph ^= 1;
+            };
+            auto fc1 = [&](int piece) {          // [128 x 128] x [64 x 128]^T -> H[piece & 1]
+                const uint32_t b_lo = slot_ready();
+                const uint32_t idesc = umma_idesc_bf16(128, 64);
+                const uint32_t a_lo = desc_lo(a2_addr);
+                if (elect_one()) {
+#pragma unroll
+                    for (uint32_t ks = 0; ks < 8; ++ks)
+                        umma_lo(tmem + TM_H + (piece & 1) * 64, a_lo + (((ks >> 2) * 16384u + (ks & 3) * 32u) >> 4),
+                                b_lo + (((ks >> 2) * 8192u + (ks & 3) * 32u) >> 4), idesc, ks > 0 ? 1u : 0u);
+                    tc_commit(&bars[BB_HFULL0 + (piece & 1)]);
+                    tc_commit(&bars[BB_EMPTY0 + pslot]);
+                }
+                __syncwarp();
+                slot_next();
+            };
 #pragma unroll 1
             for (int k = 0; k < n_local; ++k) {
+                // (the accumulators are free: the MLP group drained pieces 6, 7 of the previous tile before it stored them,
+                //  and those stores were this thread's last two triggers)
+                wait(BB_A2READY);
+                tr.ev(p, 160, k);
+                fc1(0);
+                fc1(1);
+                tr.ev(p, 140, k);
 #pragma unroll 1
-                for (int j = 0; j < 16; ++j) {
-                    const bool fc1 = j == 0 || ((j & 1) && j < 15);
-                    const int q = fc1 ? (j + 1) >> 1 : (j == 15 ? 7 : (j >> 1) - 1);
-                    if (fc1) {
-                        if (j == 0) wait(BB_A2READY);
-                        if (!first) wait(BB_HFREE);
-                        first = false;
-                    } else {
-                        wait(BB_HSREADY0 + (q & 1));
-                    }
-                    tr.ev(p, 160 + j, k);
-                    if (lane == 0) mbar_wait(&bars[BB_FULL0 + pslot], pph);
-                    __syncwarp();
-                    tc_fence_after();
-                    tr.ev(p, 120 + j, k);
-                    const uint32_t b_lo = desc_lo(ring_addr + pslot * SLOT);
-                    if (fc1) {
-                        // fc1 piece q: [128 x 128] x [64 x 128]^T -> H
-                        const uint32_t idesc = umma_idesc_bf16(128, 64);
-                        const uint32_t a_lo = desc_lo(a2_addr);
-                        if (elect_one()) {
-#pragma unroll
-                            for (uint32_t ks = 0; ks < 8; ++ks)
-                                umma_lo(tmem + TM_H, a_lo + (((ks >> 2) * 16384u + (ks & 3) * 32u) >> 4),
-                                        b_lo + (((ks >> 2) * 8192u + (ks & 3) * 32u) >> 4), idesc, ks > 0 ? 1u : 0u);
-                            tc_commit(&bars[BB_HFULL]);
-                            tc_commit(&bars[BB_EMPTY0 + pslot]);
-                        }
-                        __syncwarp();
-                    } else {
-                        // fc2 piece q: OUT (+)= GELU piece [128 x 64] (tensor memory, fp16) x [128 x 64]^T
+                for (int q = 0; q < 8; ++q) {
+                    wait(BB_HSREADY0 + (q & 1));
+                    tr.ev(p, 161 + q, k);
+                    {   // fc2 piece q: OUT (+)= GELU piece [128 x 64] (tensor memory, fp16) x [128 x 64]^T
+                        const uint32_t b_lo = slot_ready();
                         const uint32_t idesc = KASF_HALF_GELU ? umma_idesc_f16(128, 128) : umma_idesc_bf16(128, 128);
-                        const uint32_t hs = tmem + ((q & 1) ? TM_HS1 : TM_HS0);
+                        const uint32_t hs = tmem + TM_HS + (q & 1) * 32;
                         if (elect_one()) {
 #pragma unroll
                             for (uint32_t kk = 0; kk < 4; ++kk)
@@ -384,9 +386,10 @@ __global__ void __launch_bounds__(THREADS, 1) former_module_v2_kernel(const ModP
                             tc_commit(&bars[BB_EMPTY0 + pslot]);
                         }
                         __syncwarp();
+                        slot_next();
                     }
-                    tr.ev(p, 140 + j, k);
-                    if (++pslot == NSLOT) pslot = MSLOTS, pph ^= 1;
+                    if (q + 2 < 8) fc1(q + 2);
+                    tr.ev(p, 141 + q, k);
                 }
             }
             tr.done(p);
@@ -407,7 +410,7 @@ __global__ void __launch_bounds__(THREADS, 1) former_module_v2_kernel(const ModP
         long long pt0 = PROF ? clock64() : 0;
 #define PMARK2(kk)                                                    \
     do {                                                              \
-        if (PROF && mark) {                               \
+        if (PROF && mark) {                                           \
             const long long pt1 = clock64();                          \
             atomicAdd(p.prof + (kk), (unsigned long long)(pt1 - pt0)); \
             pt0 = pt1;                                                \
@@ -426,37 +429,45 @@ __global__ void __launch_bounds__(THREADS, 1) former_module_v2_kernel(const ModP
             float mean, rstd;
             float rs = 0.f;
 
-            // TMEM accumulator (this thread's 64 columns) -> bf16 rows in shared memory
-            auto drain = [&](int qkv) {
+            // N-half `nh` of Q (qkv 0), K (1) or V (2): accumulator nh, this thread's 32 columns -> bf16 in shared memory
+            auto drain = [&](int qkv, int nh) {
+                uint32_t acc[32];
+                tmem_ld32(e.tbase + TM_ACC + nh * 64 + e.half * 32, acc);
+                tmem_ld_wait();
+                const int col0 = nh * 64 + e.half * 32;
+                if (qkv == 0) {                        // query bias W_q beta_1 (LN1's affine lives in the weights)
 #pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    uint32_t acc[32];
-                    tmem_ld32(e.tbase + TM_ACC + e.half * 64 + b * 32, acc);
-                    tmem_ld_wait();
-                    if (qkv == 0) {                    // query bias W_q beta_1 (LN1's affine lives in the weights)
-#pragma unroll
-                        for (int c4 = 0; c4 < 8; ++c4) {
-                            const float4 bq = *reinterpret_cast<const float4*>(vec + V_BQ + e.half * 64 + b * 32 + c4 * 4);
-                            acc[c4 * 4 + 0] = __float_as_uint(__uint_as_float(acc[c4 * 4 + 0]) + bq.x);
-                            acc[c4 * 4 + 1] = __float_as_uint(__uint_as_float(acc[c4 * 4 + 1]) + bq.y);
-                            acc[c4 * 4 + 2] = __float_as_uint(__uint_as_float(acc[c4 * 4 + 2]) + bq.z);
-                            acc[c4 * 4 + 3] = __float_as_uint(__uint_as_float(acc[c4 * 4 + 3]) + bq.w);
-                        }
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        const float4 bq = *reinterpret_cast<const float4*>(vec + V_BQ + col0 + c4 * 4);
+                        acc[c4 * 4 + 0] = __float_as_uint(__uint_as_float(acc[c4 * 4 + 0]) + bq.x);
+                        acc[c4 * 4 + 1] = __float_as_uint(__uint_as_float(acc[c4 * 4 + 1]) + bq.y);
+                        acc[c4 * 4 + 2] = __float_as_uint(__uint_as_float(acc[c4 * 4 + 2]) + bq.z);
+                        acc[c4 * 4 + 3] = __float_as_uint(__uint_as_float(acc[c4 * 4 + 3]) + bq.w);
                     }
+                }
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        uint4 pk;
-                        pk.x = pack_bf16(__uint_as_float(acc[c * 8 + 0]), __uint_as_float(acc[c * 8 + 1]));
-                        pk.y = pack_bf16(__uint_as_float(acc[c * 8 + 2]), __uint_as_float(acc[c * 8 + 3]));
-                        pk.z = pack_bf16(__uint_as_float(acc[c * 8 + 4]), __uint_as_float(acc[c * 8 + 5]));
-                        pk.w = pack_bf16(__uint_as_float(acc[c * 8 + 6]), __uint_as_float(acc[c * 8 + 7]));
-                        if (qkv == 0) {
-                            *reinterpret_cast<uint4*>(sm + SM_A1 + tile_off_bf16(e.row, e.half * 64 + b * 32 + c * 8)) = pk;
-                        } else {
-                            const uint32_t chunk = (qkv - 1) * 16 + e.half * 8 + b * 4 + c;
-                            *reinterpret_cast<uint4*>(sm + SM_KVZ + f32_off(e.row, chunk)) = pk;
-                        }
+                for (int c = 0; c < 4; ++c) {
+                    uint4 pk;
+                    pk.x = pack_bf16(__uint_as_float(acc[c * 8 + 0]), __uint_as_float(acc[c * 8 + 1]));
+                    pk.y = pack_bf16(__uint_as_float(acc[c * 8 + 2]), __uint_as_float(acc[c * 8 + 3]));
+                    pk.z = pack_bf16(__uint_as_float(acc[c * 8 + 4]), __uint_as_float(acc[c * 8 + 5]));
+                    pk.w = pack_bf16(__uint_as_float(acc[c * 8 + 6]), __uint_as_float(acc[c * 8 + 7]));
+                    if (qkv == 0) {
+                        *reinterpret_cast<uint4*>(sm + SM_A1 + tile_off_bf16(e.row, col0 + c * 8)) = pk;
+                    } else {
+                        const uint32_t chunk = (qkv - 1) * 16 + (col0 >> 3) + c;
+                        *reinterpret_cast<uint4*>(sm + SM_KVZ + f32_off(e.row, chunk)) = pk;
                     }
+                }
+            };
+            // K then V: the halves alternate between the two accumulators, a drain runs under the next half's MMAs
+            auto drain_kv = [&]() {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    wt.wait(BB_ACCFULL0 + (i & 1));
+                    tc_fence_after();
+                    drain(1 + (i >> 1), i & 1);
+                    warp_arrive(&bars[BB_ACCFREE0 + (i & 1)], lane);
                 }
             };
 
@@ -464,7 +475,7 @@ __global__ void __launch_bounds__(THREADS, 1) former_module_v2_kernel(const ModP
                 float xv[64];
                 wt.wait(BB_ROWS);
                 PMARK2(0);
-            tr.ev(p, 0, k);
+                tr.ev(p, 0, k);
                 read_staged(sm, e, xv, row_ok);
                 if (KIND == KASF_KIND_BONE) csync();   // every staged row is in registers: the K|V drains may overwrite them
                 ln_stats<LayG0>(sm, e, xv, mean, rstd);
@@ -472,43 +483,42 @@ __global__ void __launch_bounds__(THREADS, 1) former_module_v2_kernel(const ModP
                     ln_write<false, false>(sm, SM_A1, e, xv, mean, rstd, nullptr, nullptr, row_ok);
                     warp_arrive(&bars[BB_A1READY], lane);
                     PMARK2(1);
-            tr.ev(p, 1, k);
-                    // K complete => every warp has arrived on A1READY, i.e. has read its staged rows: K|V may land there
-                    wt.wait(BB_ACCFULL);
-                    tc_fence_after();
-                    drain(1);
-                    warp_arrive(&bars[BB_ACCFREE], lane);
-                    wt.wait(BB_ACCFULL);
-                    tc_fence_after();
-                    drain(2);
-                    warp_arrive(&bars[BB_ACCFREE], lane);
+                    tr.ev(p, 1, k);
+                    // the first half of K complete => every warp has arrived on A1READY, i.e. has read its staged rows
+                    drain_kv();
                 } else if (KIND == KASF_KIND_BONE) {
                     PMARK2(1);
-            tr.ev(p, 1, k);
-                    wt.wait(BB_ACCFULL);               // K of the limb tile
-                    tc_fence_after();
-                    drain(1);
-                    warp_arrive(&bars[BB_ACCFREE], lane);
-                    wt.wait(BB_ACCFULL);               // V: the limb tile in A1 is no longer needed
-                    tc_fence_after();
-                    drain(2);
+                    tr.ev(p, 1, k);
+                    drain_kv();                        // K, V of the limb tile; afterwards A1 is free
                     ln_write<false, false>(sm, SM_A1, e, xv, mean, rstd, nullptr, nullptr, row_ok);
-                    warp_arrive(&bars[BB_A1READY], lane);   // (also: this warp's part of V has left the accumulator)
+                    warp_arrive(&bars[BB_A1READY], lane);
                 } else {
                     csync();                           // z (fp32) replaces the staged rows
                     ln_write<true, true>(sm, SM_A1, e, xv, mean, rstd, vec + V_N1W, vec + V_N1B, row_ok);
                     warp_arrive(&bars[BB_A1READY], lane);
                     PMARK2(1);
-            tr.ev(p, 1, k);
+                    tr.ev(p, 1, k);
                 }
             }
             if (KIND != KASF_KIND_GRAPH) {
-                wt.wait(BB_ACCFULL);                   // Q
+                // Q replaces LN1 in A1: both halves must be complete before the first one is drained
+                wt.wait(BB_ACCFULL0);
+                wt.wait(BB_ACCFULL1);
                 tc_fence_after();
-                drain(0);
+                drain(0, 0);
+                drain(0, 1);
+                {   // both accumulators are free for the projection
+                    fence_proxy_async();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(&bars[BB_ACCFREE0]);
+                        mbar_arrive(&bars[BB_ACCFREE1]);
+                    }
+                }
                 csync();                               // every warp reads the K|V rows of the others
                 PMARK2(2);
-            tr.ev(p, 2, k);
+                tr.ev(p, 2, k);
                 attention_core<MODE, 0>(sm, gw, lane, gsize, nrows);
                 warp_arrive(&bars[BB_A1READY], lane);
                 csync();                               // K|V are dead: the next tile's rows may land there
@@ -519,7 +529,7 @@ __global__ void __launch_bounds__(THREADS, 1) former_module_v2_kernel(const ModP
                     csync();
                 }
                 PMARK2(2);
-            tr.ev(p, 2, k);
+                tr.ev(p, 2, k);
                 // ---- aggregation  agg_i = sum_j A_ij / sqrt(d_i d_j) * z_j : this thread's 64 columns of its row
                 float ag[64];
 #pragma unroll
@@ -563,7 +573,8 @@ __global__ void __launch_bounds__(THREADS, 1) former_module_v2_kernel(const ModP
                         }
                     }
                 }
-                wt.wait(BB_ACCFULL);                   // U z done: A1 may be overwritten
+                wt.wait(BB_ACCFULL0);                  // U z done (both halves): A1 may be overwritten
+                wt.wait(BB_ACCFULL1);
                 tc_fence_after();
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
@@ -581,13 +592,16 @@ __global__ void __launch_bounds__(THREADS, 1) former_module_v2_kernel(const ModP
                 gather_rows<MODE>(p, sm, tile + (int)gridDim.x, p.in, &bars[BB_ROWS], gw, lane, 0);
                 gather_rows<MODE>(p, sm, tile + (int)gridDim.x, p.in, &bars[BB_ROWS], gw, lane, 1);
             }
-            // ---- x1 = x + ls1 * mixer -> tensor memory.  x is re-read (L2), requested before the waits
+            // ---- x1 = x + ls1 * mixer -> the output rows (L2).  This thread's columns: 32 of each accumulator half.
+            //      x is re-read (L2), requested before the waits.
             {
                 float xg[64];
+                const long long rowoff = (tok >= 0 ? tok : 0) * D;
                 if (row_ok) {
-                    const float* xrow = p.in + tok * D + e.half * 64;
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) ldg256(xrow + c * 8, xg + c * 8);
+                    for (int b = 0; b < 2; ++b)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) ldcg256(p.in + rowoff + b * 64 + e.half * 32 + c * 8, xg + b * 32 + c * 8);
                 } else {
 #pragma unroll
                     for (int i = 0; i < 64; ++i) xg[i] = 0.f;
@@ -598,23 +612,22 @@ __global__ void __launch_bounds__(THREADS, 1) former_module_v2_kernel(const ModP
                     bn_s = vec[V_BNS + node];
                     bn_t = vec[V_BNT + node];
                 }
-                if (k > 0) {
-                    wt.wait(BB_XBFREE);
-                    tc_fence_after();
-                }
-                wt.wait(BB_ACCFULL);                   // projection | += (A_hat z) V^T
-                tc_fence_after();
-                PMARK2(4);
-            tr.ev(p, 4, k);
                 const float nm = -mean * rstd;
 #pragma unroll
                 for (int b = 0; b < 2; ++b) {
+                    wt.wait(BB_ACCFULL0 + b);          // projection | += (A_hat z) V^T, N-half b
+                    tc_fence_after();
+                    if (b == 0) {
+                        PMARK2(4);
+                        tr.ev(p, 4, k);
+                    }
                     uint32_t acc[32];
-                    tmem_ld32(e.tbase + TM_ACC + e.half * 64 + b * 32, acc);
+                    tmem_ld32(e.tbase + TM_ACC + b * 64 + e.half * 32, acc);
                     tmem_ld_wait();
+                    warp_arrive(&bars[BB_ACCFREE0 + b], lane);
 #pragma unroll
                     for (int c4 = 0; c4 < 8; ++c4) {
-                        const int col = e.half * 64 + b * 32 + c4 * 4;
+                        const int col = b * 64 + e.half * 32 + c4 * 4;
                         const float4 ls = *reinterpret_cast<const float4*>(vec + V_LS1 + col);
                         const float4 bm = *reinterpret_cast<const float4*>(vec + V_BMIX + col);
                         float m0 = __uint_as_float(acc[c4 * 4 + 0]) + bm.x, m1 = __uint_as_float(acc[c4 * 4 + 1]) + bm.y,
@@ -633,15 +646,20 @@ __global__ void __launch_bounds__(THREADS, 1) former_module_v2_kernel(const ModP
                             m2 = fmaxf(z2 + ((m2 + rs * bv.z) * bn_s + bn_t), 0.f);
                             m3 = fmaxf(z3 + ((m3 + rs * bv.w) * bn_s + bn_t), 0.f);
                         }
-                        acc[c4 * 4 + 0] = __float_as_uint(fmaf(ls.x, m0, x0));
-                        acc[c4 * 4 + 1] = __float_as_uint(fmaf(ls.y, m1, x1));
-                        acc[c4 * 4 + 2] = __float_as_uint(fmaf(ls.z, m2, x2));
-                        acc[c4 * 4 + 3] = __float_as_uint(fmaf(ls.w, m3, x3));
+                        xg[b * 32 + c4 * 4 + 0] = fmaf(ls.x, m0, x0);
+                        xg[b * 32 + c4 * 4 + 1] = fmaf(ls.y, m1, x1);
+                        xg[b * 32 + c4 * 4 + 2] = fmaf(ls.z, m2, x2);
+                        xg[b * 32 + c4 * 4 + 3] = fmaf(ls.w, m3, x3);
                     }
-                    tmem_st32(e.tbase + TM_XB + e.half * 64 + b * 32, acc);
+                    if (row_ok) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) stg256(p.out + rowoff + b * 64 + e.half * 32 + c * 8, xg + b * 32 + c * 8);
+                    }
                 }
-                tmem_st_wait();
-                warp_arrive2(&bars[BB_X1READY], &bars[BB_ACCFREE], lane);
+                // the MLP group must have started the previous tile before X1READY completes another phase
+                if (k > 0) wt.wait(BB_X1TAKEN);
+                __threadfence_block();
+                warp_arrive(&bars[BB_X1READY], lane);
             }
             PMARK2(5);
             tr.ev(p, 5, k);
@@ -665,20 +683,20 @@ __global__ void __launch_bounds__(THREADS, 1) former_module_v2_kernel(const ModP
             const int nrows = tile_rows<MODE>(p, tile);
             const bool row_ok = e.row < nrows;
             const long long tok = row_ok ? row_token<MODE>(p, tile, e.row) : -1;
+            float* orow = p.out + (tok >= 0 ? tok : 0) * D + e.half * 64;
             // ---- LN2(x1) -> A2
             wt.wait(BB_X1READY);
-            tc_fence_after();
+            warp_arrive(&bars[BB_X1TAKEN], lane);
             PMARK2(8);
             tr.ev(p, 230, k);
             {
                 float xv[64];
+                if (row_ok) {
 #pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    uint32_t xr[32];
-                    tmem_ld32(e.tbase + TM_XB + e.half * 64 + b * 32, xr);
-                    tmem_ld_wait();
+                    for (int c = 0; c < 8; ++c) ldcg256(orow + c * 8, xv + c * 8);
+                } else {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) xv[b * 32 + i] = __uint_as_float(xr[i]);
+                    for (int i = 0; i < 64; ++i) xv[i] = 0.f;
                 }
                 float mean, rstd;
                 ln_stats<LayG1>(sm, e, xv, mean, rstd);
@@ -691,14 +709,13 @@ __global__ void __launch_bounds__(THREADS, 1) former_module_v2_kernel(const ModP
             // ---- eight GELU epilogues: fc1 accumulator (64 hidden columns) -> 2*GELU -> packed fp16 pairs in tensor memory
 #pragma unroll 1
             for (int q = 0; q < 8; ++q) {
-                wt.wait(BB_HFULL);
+                wt.wait(BB_HFULL0 + (q & 1));
                 tc_fence_after();
                 PMARK2(10);
                 tr.ev(p, 200 + q, k);
                 uint32_t acc[32];
-                tmem_ld32(e.tbase + TM_H + e.half * 32, acc);
+                tmem_ld32(e.tbase + TM_H + (q & 1) * 64 + e.half * 32, acc);
                 tmem_ld_wait();
-                warp_arrive(&bars[BB_HFREE], lane);    // the next fc1 piece may overwrite the accumulator
                 tr.ev(p, 210 + q, k);
                 uint32_t hs[16];
 #if KASF_HALF_GELU
@@ -734,25 +751,28 @@ __global__ void __launch_bounds__(THREADS, 1) former_module_v2_kernel(const ModP
                 }
 #endif
                 PMARK2(11);
-                wt.wait((q & 1) ? BB_HSFREE1 : BB_HSFREE0);   // fc2 of piece q-2 has read this buffer
+                wt.wait(BB_HSFREE0 + (q & 1));         // fc2 of piece q-2 has read this buffer
                 tc_fence_after();
                 PMARK2(12);
-                tmem_st16(e.tbase + ((q & 1) ? TM_HS1 : TM_HS0) + e.half * 16, hs);
+                tmem_st16(e.tbase + TM_HS + (q & 1) * 32 + e.half * 16, hs);
                 tmem_st_wait();
-                warp_arrive(&bars[(q & 1) ? BB_HSREADY1 : BB_HSREADY0], lane);
+                warp_arrive(&bars[BB_HSREADY0 + (q & 1)], lane);
                 tr.ev(p, 220 + q, k);
             }
-            // ---- out = x1 + ls2 * (acc + b2): 256-bit stores of this thread's 64 columns
+            // ---- out = x1 + ls2 * (acc + b2): x1 re-read (L2), 256-bit stores of this thread's 64 columns
+            float xr[64];
+            if (row_ok) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) ldcg256(orow + c * 8, xr + c * 8);
+            }
             wt.wait(BB_OUTFULL);
             tc_fence_after();
             PMARK2(13);
             {
-                float* orow = p.out + (tok >= 0 ? tok : 0) * D + e.half * 64;
 #pragma unroll
                 for (int b = 0; b < 2; ++b) {
-                    uint32_t acc[32], xr[32];
+                    uint32_t acc[32];
                     tmem_ld32(e.tbase + TM_OUT + e.half * 64 + b * 32, acc);
-                    tmem_ld32(e.tbase + TM_XB + e.half * 64 + b * 32, xr);
                     tmem_ld_wait();
 #pragma unroll
                     for (int c8 = 0; c8 < 4; ++c8) {
@@ -763,16 +783,17 @@ __global__ void __launch_bounds__(THREADS, 1) former_module_v2_kernel(const ModP
                             const float4 ls = *reinterpret_cast<const float4*>(vec + V_LS2 + col + h4 * 4);
                             const float4 b2 = *reinterpret_cast<const float4*>(vec + V_B2 + col + h4 * 4);
                             const int i = c8 * 8 + h4 * 4;
-                            o[h4 * 4 + 0] = fmaf(ls.x, __uint_as_float(acc[i + 0]) + b2.x, __uint_as_float(xr[i + 0]));
-                            o[h4 * 4 + 1] = fmaf(ls.y, __uint_as_float(acc[i + 1]) + b2.y, __uint_as_float(xr[i + 1]));
-                            o[h4 * 4 + 2] = fmaf(ls.z, __uint_as_float(acc[i + 2]) + b2.z, __uint_as_float(xr[i + 2]));
-                            o[h4 * 4 + 3] = fmaf(ls.w, __uint_as_float(acc[i + 3]) + b2.w, __uint_as_float(xr[i + 3]));
+                            o[h4 * 4 + 0] = fmaf(ls.x, __uint_as_float(acc[i + 0]) + b2.x, xr[b * 32 + i + 0]);
+                            o[h4 * 4 + 1] = fmaf(ls.y, __uint_as_float(acc[i + 1]) + b2.y, xr[b * 32 + i + 1]);
+                            o[h4 * 4 + 2] = fmaf(ls.z, __uint_as_float(acc[i + 2]) + b2.z, xr[b * 32 + i + 2]);
+                            o[h4 * 4 + 3] = fmaf(ls.w, __uint_as_float(acc[i + 3]) + b2.w, xr[b * 32 + i + 3]);
                         }
                         if (tok >= 0) stg256(orow + b * 32 + c8 * 8, o);
                     }
                 }
             }
-            warp_arrive(&bars[BB_XBFREE], lane);       // x1 rows and the fc2 accumulator are drained
+            // (the fc2 accumulator is drained: the next tile's first fc2 piece follows this thread's next HSREADY)
+            tc_fence_before();
             PMARK2(14);
             tr.ev(p, 232, k);
         }

@@ -21,6 +21,8 @@ import math
 from collections import OrderedDict
 from typing import Dict, Optional
 
+import threading
+
 import torch
 from torch import nn
 
@@ -164,7 +166,11 @@ class KASportsFormer(nn.Module):
         self.rep_logit = nn.Sequential(OrderedDict([("fc", nn.Linear(dim_feat, dim_rep)),
                                                     ("act", nn.Tanh())]))
         self.head = nn.Linear(dim_rep, dim_out)
-        self._packed: Dict[int, tuple] = {}      # device index -> (signature, packed blob tensor)
+        self._packed: Dict[int, tuple] = {}      # device index -> (signature, packed blob, fp32 image or None)
+        self._pack_lock = threading.Lock()       # (shared with nn.DataParallel replicas: they copy __dict__ shallowly)
+        # "fast": bf16 tensor-core operands (default) | "exact": the reference's fp32 arithmetic on CUDA cores,
+        # an order of magnitude slower -- for checking a checkpoint's accuracy (README, "Precision")
+        self.precision = "fast"
 
     # -- weight packing -------------------------------------------------------------------------
     def _signature(self):
@@ -190,16 +196,20 @@ class KASportsFormer(nn.Module):
         """Force re-packing of the weights on next forward (after in-place edits via `.data`)."""
         self._packed.clear()
 
-    def packed_weights(self, device: torch.device) -> torch.Tensor:
+    def packed_weights(self, device: torch.device, with_image: bool = False):
+        """Kernel-ready blob of the current weights on `device` (cached per device, re-packed when a parameter
+        changes); with_image: also the fp32 weight image that precision="exact" reads.  Thread-safe: nn.DataParallel
+        replicas share this cache and call from one thread per device."""
         idx = device.index if device.index is not None else torch.cuda.current_device()
         sig = self._signature()
-        hit = self._packed.get(idx)
-        if hit is not None and hit[0] == sig:
-            return hit[1]
-        state = {k: v for k, v in self.state_dict().items() if v.is_floating_point()}
-        blob = _capi.pack_state(self.cfg, state, torch.device("cuda", idx))
-        self._packed[idx] = (sig, blob)
-        return blob
+        with self._pack_lock:
+            hit = self._packed.get(idx)
+            if hit is not None and hit[0] == sig and (hit[2] is not None or not with_image):
+                return (hit[1], hit[2]) if with_image else hit[1]
+            state = {k: v for k, v in self.state_dict().items() if v.is_floating_point()}
+            blob, img = _capi.pack_state(self.cfg, state, torch.device("cuda", idx), keep_image=True)
+            self._packed[idx] = (sig, blob, img if with_image else None)
+            return (blob, img) if with_image else blob
 
     # -- forward --------------------------------------------------------------------------------
     @torch.no_grad()
@@ -212,6 +222,9 @@ class KASportsFormer(nn.Module):
             raise RuntimeError("kasportsformer_b200 has no CPU path: move the input (and the model) "
                                "to a B200 device")
         x = x.contiguous().float()
+        if self.precision == "exact":
+            blob, img = self.packed_weights(x.device, with_image=True)
+            return _capi.forward(self.cfg, blob, x, return_rep, precision="exact", image=img)
         blob = self.packed_weights(x.device)
         return _capi.forward(self.cfg, blob, x, return_rep)
 
@@ -242,14 +255,18 @@ class GraphedForward:
         self.cfg, self.batch, self.return_rep = dict(model.cfg), int(batch), bool(return_rep)
         self._blob = model.packed_weights(dev)
         self._x = torch.zeros(self.batch, self.cfg["n_frames"], 17, 3, dtype=torch.float32, device=dev)
+        # the graph bakes in raw pointers: it owns its workspace and its forward context (side streams + events) instead
+        # of borrowing the per-caller cached ones, which another forward on a recycled stream handle could replace
+        self._ws = torch.empty(_capi.workspace_bytes(self.cfg, self.batch), dtype=torch.uint8, device=dev)
+        self._ctx = _capi.ForwardContext(dev)
         self._graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            _capi.forward(self.cfg, self._blob, self._x, self.return_rep)     # workspace allocation outside capture
+            _capi.forward(self.cfg, self._blob, self._x, self.return_rep, ws=self._ws, ctx=self._ctx)   # warm-up
             side.synchronize()
             with torch.cuda.graph(self._graph, stream=side):
-                self._y = _capi.forward(self.cfg, self._blob, self._x, self.return_rep)
+                self._y = _capi.forward(self.cfg, self._blob, self._x, self.return_rep, ws=self._ws, ctx=self._ctx)
         torch.cuda.current_stream(dev).wait_stream(side)
 
     @torch.no_grad()

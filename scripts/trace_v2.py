@@ -17,9 +17,10 @@ def name(tag):
     if tag < 6: return ["G0 rows landed", "G0 LN1 written", "G0 qkv drained", "G0 core done", "G0 epilogue waits over", "G0 epilogue done"][tag]
     if 100 <= tag < 110: return f"ISS mixer op {tag-100} triggers ready"
     if 110 <= tag < 120: return f"ISS mixer op {tag-110} issued"
-    if 120 <= tag < 140: return f"ISS mlp op {tag-120} weights ready"
-    if 140 <= tag < 160: return f"ISS mlp op {tag-140} issued"
-    if 160 <= tag < 180: return f"ISS mlp op {tag-160} triggers ready"
+    if tag == 140: return "ISS mlp fc1(0), fc1(1) issued"
+    if 141 <= tag < 160: return f"ISS mlp fc2({tag-141}) + fc1({tag-139}) issued"
+    if tag == 160: return "ISS mlp LN2 ready"
+    if 161 <= tag < 180: return f"ISS mlp GELU piece {tag-161} ready"
     if 200 <= tag < 210: return f"G1 HFULL seen q={tag-200}"
     if 210 <= tag < 220: return f"G1 H loaded q={tag-210}"
     if 220 <= tag < 230: return f"G1 GELU stored q={tag-220}"

@@ -31,7 +31,7 @@ def test_header_symbols_exported(lib):
     assert declared == set(_capi.exported_symbols()), declared ^ set(_capi.exported_symbols())
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.kasf_version() == 1
+    assert lib.kasf_version() == 2
     assert b"sm_100" in lib.kasf_strerror(-3)
 
 

@@ -106,6 +106,21 @@ def test_forward_micro_batched_large_B():
     assert torch.isfinite(y).all()
 
 
+def test_forward_two_tiles_flag_and_plain_entry():
+    """KASF_FLAG_TWO_TILES through kasf_forward_ex (falls back per module where it does not apply) and the stateless
+    kasf_forward (no context: one stream) agree with the default forward to operand-rounding noise."""
+    cfg = dict(n_layers=2, n_frames=27, dim_feat=128, dim_rep=512, num_heads=8, mlp_ratio=4, num_joints=17,
+               neighbour_num=4)
+    m = _model(cfg, 6, "stress")
+    x = synthetic.make_clips(9, 27, 4, "det").to(DEV)
+    y = m(x)
+    blob = m.packed_weights(x.device)
+    y2 = _capi.forward(cfg, blob, x, two_tiles=True)
+    assert (y2 - y).abs().max().item() <= 2e-3
+    y3 = _capi.forward(cfg, blob, x, branch_streams=False)
+    assert torch.equal(y3, y)
+
+
 def test_graphed_forward_matches_stream_launches():
     """CUDA-graph replay of the forward (fixed batch) is bit-identical to the stream-launched forward."""
     cfg = dict(n_layers=2, n_frames=27, dim_feat=128, dim_rep=512, num_heads=8, mlp_ratio=4, num_joints=17,

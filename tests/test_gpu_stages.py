@@ -113,6 +113,17 @@ def test_former_module(br, kind, mode, T, B):
         assert err_rows.max().item() <= 4e-3, f"emulated-oracle error {err_rows.max().item()}"
     err_f = ((out - ref).abs().amax(dim=-1).reshape(-1) / upd)
     assert err_f.quantile(0.99).item() <= 3e-2, f"fp32-oracle error {err_f.quantile(0.99).item()}"
+    if mode == "spatial" or T <= 32:
+        # the opt-in two-tiles-in-flight kernel (KASF_FLAG_TWO_TILES; bone modules through limb tiles): same arithmetic
+        out2 = _capi.former_module(cfg, blob, 0, kind, mode, v.to(DEV), XL.to(DEV), two_tiles=True).cpu()
+        err2 = (out2 - ref_q).abs().amax(dim=-1).reshape(-1) / upd
+        if kind == "graph" and mode == "temporal":
+            assert (err2 > 2e-3).float().mean().item() <= 0.005 and err2.median().item() <= 5e-4
+        else:
+            assert err2.max().item() <= 4e-3, f"two-tiles kernel vs emulated oracle {err2.max().item()}"
+    else:
+        with pytest.raises(_capi.KasfError):
+            _capi.former_module(cfg, blob, 0, kind, mode, v.to(DEV), XL.to(DEV), two_tiles=True)
     if kind == "bone":
         # the path kasf_forward takes: K|V operand from the pre-normalised bf16 limb tiles (one bulk copy per tile)
         out_lt = _capi.former_module(cfg, blob, 0, kind, mode, v.to(DEV), XL.to(DEV), use_limb_tiles=True).cpu()
