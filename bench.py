@@ -18,6 +18,14 @@ exchange of the path).  Rank 0 prints ONE JSON line.
                event after every launch (branches serialised on one stream; `serialised_ms_per_step`) and the
                per-launch times come from that pass
   cpu_baseline oracle port of the reference forward timed on the host cores (bounded sample)
+  gpu_eager_baseline (N = 1) the same eager PyTorch forward (oracle port: the ATen calls the reference issues -> cuBLAS /
+               ATen kernels) on the SAME B200, same B x T input, in fp32, with TF32 allowed, and under bf16 autocast:
+               the bar a hand-written path has to beat on this box
+  sweep ...... clips/s of the forward at T = 81 and T = 243 (256 clips per GPU), same process, every N
+               (BASELINE.json configs[3])
+  parity ..... max |dy| and the MPJPE difference in mm against the reference golden with trained-like magnitudes
+               (tests/golden/trained_like_L26_T27.npz) for precision "fast" (what `value` measures) and "exact",
+               and the exact mode's clips/s
 
 `--impl reference` times the reference's CPU implementation of the path: /root/reference does not travel to
 the GPU box and is pure Python/PyTorch, so this arm runs the oracle port (oracle/kasf_oracle.py, the same
@@ -143,13 +151,133 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"KASportsFormer sportspose-det T={T} J=17 forward, batch {args.batch} per GPU", "frames": T},
+        "config": {"workload": f"KASportsFormer sportspose-det T={T} J=17 forward, batch {args.batch} per GPU "
+                               "(BASELINE.json configs[1]), default-init weights", "frames": T, "batch_per_gpu": args.batch,
+                   "parallelism": f"dp{args.gpus} (batch-sharded clips, all_gather of MPJPE sums)",
+                   "l2": f"per-step working set {6 * args.batch * T * 17 * 512 / 1e6:.0f} MB of fp32 streams > 126 MB L2 (no flush needed)"},
         "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
+# ------------------------------------------------------------------ same-box eager baseline (oracle port on the GPU)
+def gpu_eager_rates(T: int, B: int, dev):
+    """Eager PyTorch forward of the reference's op sequence on the same GPU: clips/s in fp32 (TF32 off: torch's default
+    for matmul), with TF32 allowed, and under bf16 autocast.  CUDA events, 1 warm-up + 2 timed forwards each."""
+    from kasportsformer_b200 import synthetic
+    from oracle import kasf_oracle as O
+    cfg = dict(CFG, n_frames=T)
+    state = {k: v.to(dev) for k, v in synthetic.make_state(cfg, 0, "default").items()}
+    x = synthetic.make_clips(B, T, 0, "det").to(dev)
+    ocfg = O.default_config(n_frames=T)
+    out = {}
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(2):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return 2 * B / (a.elapsed_time(b) / 1e3)
+
+    old = torch.backends.cuda.matmul.allow_tf32
+    try:
+        with torch.no_grad():
+            torch.backends.cuda.matmul.allow_tf32 = False
+            out["fp32"] = timed(lambda: O.forward(state, x, ocfg))
+            torch.backends.cuda.matmul.allow_tf32 = True
+            out["tf32"] = timed(lambda: O.forward(state, x, ocfg))
+            torch.backends.cuda.matmul.allow_tf32 = False
+
+            def ac():
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    O.forward(state, x, ocfg)
+            out["bf16_autocast"] = timed(ac)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    return {"unit": "clips/s", "batch": B, "frames": T, **{k: round(v, 1) for k, v in out.items()},
+            "what": "oracle port of the reference forward (eager ATen / cuBLAS) on the same B200, inputs resident, CUDA events"}
+
+
+def parity_report(dev):
+    """Both precision modes against the reference golden with trained-like magnitudes (26 layers, T = 27)."""
+    import numpy as np
+    from kasportsformer_b200 import KASportsFormer, synthetic
+    from oracle import metrics_oracle as MO
+    p = os.path.join(ROOT, "tests", "golden", "trained_like_L26_T27.npz")
+    if not os.path.exists(p):
+        return None
+    z = np.load(p)
+    meta = json.loads(str(z["meta"]))
+    cfg = meta["cfg"]
+    m = KASportsFormer(n_layers=cfg["n_layers"], num_heads=8, n_frames=cfg["n_frames"])
+    m.load_state_dict(synthetic.make_state(cfg, meta["seed"], meta["regime"]))
+    m = m.to(dev).eval()
+    x = synthetic.make_clips(meta["B"], 27, meta["clip_seed"], meta["kind"]).to(dev)
+    gt, factor, res, _ = synthetic.make_labels(meta["B"], 27, seed=meta["label_seed"], n_actions=1)
+    mm = 1920.0 / 2.0
+    rep = {"golden": "tests/golden/trained_like_L26_T27.npz (unmodified reference, layer scales 0.05-0.15)",
+           "unit": "mm (normalised units x 960: res_w = 1920, factor 1)"}
+    for mode in ("fast", "exact"):
+        m.precision = mode
+        y = m(x).cpu().numpy()
+        r = MO.evaluate(y, res.numpy().astype(np.float64), factor.numpy(), gt.numpy())
+        rep[mode] = {"max_abs_dy_mm": round(float(np.abs(y - z["y"]).max() * mm), 5),
+                     "mean_abs_dy_mm": round(float(np.abs(y - z["y"]).mean() * mm), 5),
+                     "d_mpjpe_mm": round(abs(r["mpjpe"] - float(z["mpjpe"])), 6),
+                     "d_p_mpjpe_mm": round(abs(r["p_mpjpe"] - float(z["p_mpjpe"])), 6)}
+    # exact-mode throughput (64 clips, default-init 26 layers)
+    m.precision = "exact"
+    xb = synthetic.make_clips(64, 27, 1, "det").to(dev)
+    m(xb)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    m(xb)
+    b.record()
+    torch.cuda.synchronize()
+    rep["exact_clips_per_s"] = round(64 / (a.elapsed_time(b) / 1e3), 1)
+    return rep
+
+
 # ------------------------------------------------------------------ GPU arm
+def sweep_point(T: int, B: int, dev, world, dist, steps: int = 3):
+    """clips/s of the forward at another sequence length (inputs resident, CUDA events, max over ranks)."""
+    from kasportsformer_b200 import KASportsFormer, _capi, synthetic
+    cfg = dict(CFG, n_frames=T)
+    model = KASportsFormer(n_layers=26, num_heads=8, n_frames=T)
+    model.load_state_dict(synthetic.make_state(cfg, 0, "default"))
+    model = model.to(dev).eval()
+    blob = model.packed_weights(dev)
+    rank = int(os.environ.get("RANK", "0"))
+    x = synthetic.make_clips(B, T, seed=rank, kind="det").to(dev)
+    y = torch.empty(B, T, 17, 3, device=dev)
+    for _ in range(3):
+        _capi.forward_into(cfg, blob, x, y, None)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        _capi.forward_into(cfg, blob, x, y, None)
+    b.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item() / steps
+    v = world * B / (ms / 1e3)
+    pk = peaks()
+    del model, blob, x, y
+    torch.cuda.empty_cache()
+    return {"frames": T, "batch_per_gpu": B, "value": round(v, 1), "unit": "clips/s", "ms_per_step": round(ms, 3),
+            "steps": steps, "whole_forward_frac": round(v / world * flops_per_clip(T) / 1e12 / pk["bf16"], 4)}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from kasportsformer_b200 import KASportsFormer, _capi, synthetic
@@ -245,6 +373,14 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
 
+    # ---- the other sequence lengths of BASELINE.json configs[3], every N (all ranks take part)
+    sweep = []
+    if T == 27 and not args.no_sweep:
+        del model, x, y
+        torch.cuda.empty_cache()
+        for Ts, Bs in ((81, 256), (243, 256)):
+            sweep.append(sweep_point(Ts, Bs, dev, world, dist if world > 1 else None))
+
     if rank == 0:
         pk = peaks()
         value = world * B * args.steps / (ms / 1e3)
@@ -303,6 +439,11 @@ def run_ours(args):
                          "other_ms": {"features": round(feat_ms, 4), "head": round(head_ms, 4)},
                          "whole_forward_frac": value / world * flops_per_clip(T) / 1e12 / pk["bf16"]},
         }
+        if sweep:
+            out["sweep"] = sweep
+        if world == 1 and not args.no_extras:
+            out["gpu_eager_baseline"] = gpu_eager_rates(T, B, dev)
+            out["parity"] = parity_report(dev)
         if world == 1 and not args.no_cpu:
             v, secs = cpu_forward_rate(T, 32, 2)
             out["cpu_baseline"] = {"value": v, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port",
@@ -323,6 +464,8 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--frames", type=int, default=27)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the T = 81 / 243 sweep points")
+    ap.add_argument("--no-extras", action="store_true", help="skip the same-box eager baseline and the parity report")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -216,7 +216,7 @@ def gcn_mixer(state: State, pre: str, z: Tensor, mode: str, neighbour_num: int,
         adj = temporal_adjacency(g, neighbour_num) if adj_override is None else adj_override
     else:
         g = z.reshape(B * T, J, C)
-        adj = skeleton_adjacency(z.dtype).unsqueeze(0)
+        adj = skeleton_adjacency(z.dtype).to(z.device).unsqueeze(0)
     deg = adj.sum(-1)                                         # row sums, graph.py:81
     dis = deg ** -0.5
     norm_adj = dis.unsqueeze(-1) * adj * dis.unsqueeze(-2)   # D^-1/2 A D^-1/2, graph.py:86-88
