@@ -27,6 +27,7 @@ import torch
 from torch import nn
 
 from . import _capi
+from . import ops as _ops  # noqa: F401  (registers torch.ops.kasf.*)
 from .skeleton import LIMB_GROUPS, LIMB_HIDDEN, LIMB_CHANNEL_NAMES
 
 
@@ -222,11 +223,13 @@ class KASportsFormer(nn.Module):
             raise RuntimeError("kasportsformer_b200 has no CPU path: move the input (and the model) "
                                "to a B200 device")
         x = x.contiguous().float()
-        if self.precision == "exact":
-            blob, img = self.packed_weights(x.device, with_image=True)
-            return _capi.forward(self.cfg, blob, x, return_rep, precision="exact", image=img)
-        blob = self.packed_weights(x.device)
-        return _capi.forward(self.cfg, blob, x, return_rep)
+        if self.precision not in ("fast", "exact"):
+            raise ValueError(f'precision must be "fast" or "exact", got {self.precision!r}')
+        exact = self.precision == "exact"
+        blob, img = self.packed_weights(x.device, with_image=True) if exact else (self.packed_weights(x.device), None)
+        # the registered custom op (kasportsformer_b200/ops.py) -> ctypes -> kasf_forward_ex
+        return torch.ops.kasf.forward(x, blob, img, self.cfg["n_layers"], self.cfg["n_frames"], bool(return_rep),
+                                      1 if exact else 0, 0)
 
     def graphed(self, batch: int, return_rep: bool = False) -> "GraphedForward":
         """The forward for a fixed batch size captured once into a CUDA graph (the 186 launches of `kasf_forward`,

@@ -215,6 +215,42 @@ def save_trained_like_fixture():
     print("trained_like_L26_T27: |y| mean", y.abs().mean().item(), "MPJPE", np.mean(mp), "P-MPJPE", np.mean(pmp))
 
 
+def save_eval_loop_fixture():
+    """The UNMODIFIED evaluation loop (train_and_evaluate_sp.py:27-149) driving the REAL reference model (26 layers,
+    trained-like magnitudes) over a synthetic loader of two batches, with and without the flip TTA: what a drop-in
+    module has to reproduce when the scripts swap it in.  Also checks oracle/eval_loop_oracle.py (the restatement the GPU
+    test runs, since the reference checkout does not travel to the GPU box) against the real loop on the real model."""
+    from oracle import eval_loop_oracle as ELO
+    cfg = cfg_of()
+    state = synthetic.make_state(cfg, 43, "stress")
+    m = ref_shim.build_reference(cfg)
+    m.load_state_dict(state, strict=True)
+    ev, ED = ref_shim.reference_eval_loop()
+    B = 6
+    x = synthetic.make_clips(B, 27, 23, "det")
+    gt, factor, res, _ = synthetic.make_labels(B, 27, seed=11, n_actions=1)
+    res[3:] = torch.tensor([1216.0, 1936.0])
+    actions = ["jump", "throw", "jump", "kick", "throw", "jump"]
+    loader = [(x[:3], gt[:3], factor[:3], actions[:3], res[:3]), (x[3:], gt[3:], factor[3:], actions[3:], res[3:])]
+
+    class Log:
+        def info(self, *_):
+            pass
+    out = dict(meta=json.dumps(dict(cfg=cfg, seed=43, regime="stress", B=B, clip_seed=23, kind="det", label_seed=11,
+                                    actions=actions)))
+    for flip in (False, True):
+        r = ev(ED(num_joints=17, flip=flip, eval_only=True), m, loader, "cpu", 0, Log())
+        o = ELO.evaluate_loop(m, loader, "cpu", flip)
+        for k in ("mpjpe", "p_mpjpe", "acceleration_error"):
+            assert abs(r[k] - o[k]) <= 1e-3, (k, r[k], o[k])
+        assert np.abs(np.asarray(r["mpjpe_joint"]) - o["mpjpe_joint"]).max() <= 1e-3
+        tag = "flip" if flip else "noflip"
+        out[f"eval_{tag}"] = np.array([r["mpjpe"], r["p_mpjpe"], r["acceleration_error"]])
+        out[f"eval_{tag}_joint"] = np.asarray(r["mpjpe_joint"])
+    np.savez_compressed(os.path.join(OUT, "eval_loop_real_model.npz"), **out)
+    print("eval_loop_real_model:", out["eval_noflip"], out["eval_flip"])
+
+
 def _reference_functions(rel_path, names):
     """Compile selected top-level functions of a reference file (whose imports are not available here: cv2, lib.*)
     in a numpy-only namespace.  The function bodies are executed as they are in the read-only checkout."""
@@ -299,6 +335,7 @@ def main():
     torch.set_num_threads(8)
     if "--trained-like" in sys.argv:
         save_trained_like_fixture()
+        save_eval_loop_fixture()
         return
     if "--io-only" in sys.argv:
         save_serving_fixture()
@@ -309,6 +346,7 @@ def main():
     save_refinit_fixture()
     save_metrics_fixture()
     save_trained_like_fixture()
+    save_eval_loop_fixture()
     # acceptance regime: default init, full depth
     save_stage_fixture("full_default_T27.npz", cfg_of(), seed=0, regime="default", B=1, clip_seed=0, kind="det",
                        per_module=False)

@@ -10,3 +10,4 @@ run t3_modules tests/test_gpu_stages.py -k "former_module"
 run t4_forward tests/test_gpu_forward.py
 run t5_io tests/test_gpu_io.py
 run t6_precision tests/test_gpu_precision.py
+run t7_dropin tests/test_gpu_dropin.py
