@@ -106,12 +106,6 @@ __device__ __forceinline__ void umma_ts_lo(uint32_t tmem_d, uint32_t tmem_a, uin
         "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI)
         : "memory");
 }
-// one lane of a converged warp
-__device__ __forceinline__ bool elect_one() {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(ok));
-    return ok != 0;
-}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),

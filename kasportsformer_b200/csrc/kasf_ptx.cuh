@@ -81,6 +81,13 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
         : "memory");
 }
 
+// one lane of a converged warp (elect.sync)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(ok));
+    return ok != 0;
+}
+
 // ---------------------------------------------------------------- 256-bit global accesses (LDG/STG.E.256)
 // one full 32-byte sector per thread and instruction; addresses must be 32-byte aligned
 __device__ __forceinline__ void ldg256(const float* p, float* v) {
