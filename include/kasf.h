@@ -223,6 +223,8 @@ int kasf_head(const kasf_config* cfg, const void* packed_dev, const float* X_dev
  *   sums_dev     float64 [n_actions, KASF_METRIC_COLS]: ACCUMULATED (atomicAdd) per-action sums:
  *                col 0 sum MPJPE(frames), 1 sum P-MPJPE, 2 sum accel-error, 3 #frames, 4 #accel
  *                frames, 5..21 sum per-joint error.  Caller zeroes it and reduces across ranks.
+ *                A clip whose action index is outside [0, n_actions) is a caller error: it is SKIPPED (never folded
+ *                into another action), so column 3 then sums to fewer than B*T frames.
  *   per_frame_dev float64 [B,T,3] or NULL: per-frame (mpjpe, p_mpjpe, accel) for tests.        */
 #define KASF_METRIC_COLS 22
 int kasf_metrics(int T, const float* pred_dev, const float* pred_flip_dev, const float* gt_dev,

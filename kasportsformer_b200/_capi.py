@@ -132,8 +132,10 @@ def _check(code: int, what: str):
 
 def check_config_supported(cfg: dict):
     """Host-side mirror of the C validation (include/kasf.h, kasf_config)."""
-    fixed = dict(dim_feat=128, dim_rep=512, num_heads=8, mlp_ratio=4, num_joints=17, neighbour_num=4)
+    fixed = dict(dim_feat=128, dim_rep=512, mlp_ratio=4, num_joints=17, neighbour_num=4)
     bad = [f"{k}={cfg[k]} (built for {v})" for k, v in fixed.items() if cfg[k] != v]
+    if cfg["num_heads"] not in (4, 8):
+        bad.append(f"num_heads={cfg['num_heads']} (8: all kernels; 4: precision='exact' only)")
     if not (1 <= cfg["n_layers"] <= 1024):
         bad.append(f"n_layers={cfg['n_layers']}")
     if not (4 <= cfg["n_frames"] <= 243):

@@ -178,7 +178,7 @@ int kasf_kinematic_features(const kasf_config* cfg, const void* packed_dev, cons
 int kasf_former_module_ws(const kasf_config* cfg, const void* packed_dev, int layer, int kind, int mode,
                           const float* in_dev, const float* XL_dev, float* out_dev, int B, void* scratch_dev,
                           size_t scratch_bytes, void* stream) {
-    int rc = config_ok(cfg);
+    int rc = fast_config_ok(cfg);
     if (rc) return rc;
     if (!packed_dev || !in_dev || !out_dev || B < 0 || layer < 0 || layer >= cfg->n_layers) return KASF_EINVAL;
     if ((rc = device_ok())) return rc;
@@ -202,7 +202,7 @@ int kasf_limb_tiles(const kasf_config* cfg, const float* XL_dev, void* limb_tile
 int kasf_former_module_lt(const kasf_config* cfg, const void* packed_dev, int layer, int kind, int mode,
                           const float* in_dev, const float* XL_dev, const void* limb_tiles_dev, float* out_dev, int B,
                           void* scratch_dev, size_t scratch_bytes, void* stream) {
-    int rc = config_ok(cfg);
+    int rc = fast_config_ok(cfg);
     if (rc) return rc;
     if (!packed_dev || !in_dev || !out_dev || B < 0 || layer < 0 || layer >= cfg->n_layers) return KASF_EINVAL;
     if ((rc = device_ok())) return rc;
@@ -213,7 +213,7 @@ int kasf_former_module_lt(const kasf_config* cfg, const void* packed_dev, int la
 int kasf_former_module_ex(const kasf_config* cfg, const void* packed_dev, int layer, int kind, int mode,
                           const float* in_dev, const float* XL_dev, const void* limb_tiles_dev, float* out_dev, int B,
                           void* scratch_dev, size_t scratch_bytes, uint32_t flags, void* stream) {
-    int rc = config_ok(cfg);
+    int rc = fast_config_ok(cfg);
     if (rc) return rc;
     if (!packed_dev || !in_dev || !out_dev || B < 0 || layer < 0 || layer >= cfg->n_layers) return KASF_EINVAL;
     if ((rc = device_ok())) return rc;
@@ -229,7 +229,7 @@ int kasf_former_module(const kasf_config* cfg, const void* packed_dev, int layer
 int kasf_former_module_profiled(const kasf_config* cfg, const void* packed_dev, int layer, int kind, int mode,
                                 const float* in_dev, const float* XL_dev, float* out_dev, int B, void* stream,
                                 unsigned long long* phase_cycles_dev) {
-    int rc = config_ok(cfg);
+    int rc = fast_config_ok(cfg);
     if (rc) return rc;
     if (!packed_dev || !in_dev || !out_dev || !phase_cycles_dev || B < 0 || layer < 0 || layer >= cfg->n_layers)
         return KASF_EINVAL;
@@ -241,7 +241,7 @@ int kasf_former_module_profiled(const kasf_config* cfg, const void* packed_dev, 
 int kasf_former_module_profiled_lt(const kasf_config* cfg, const void* packed_dev, int layer, int kind, int mode,
                                    const float* in_dev, const float* XL_dev, const void* limb_tiles_dev, float* out_dev,
                                    int B, void* stream, unsigned long long* phase_cycles_dev) {
-    int rc = config_ok(cfg);
+    int rc = fast_config_ok(cfg);
     if (rc) return rc;
     if (!packed_dev || !in_dev || !out_dev || !phase_cycles_dev || B < 0 || layer < 0 || layer >= cfg->n_layers)
         return KASF_EINVAL;
@@ -288,6 +288,7 @@ static int forward_impl(const kasf_config* cfg, const void* packed_dev, const fl
         return exact_forward(cfg, opts->image_dev, (const uint8_t*)packed_dev, x_dev, y_dev, rep_dev, B, ws_dev, ws_bytes, st);
     }
     if (!packed_dev) return KASF_EINVAL;
+    if ((rc = fast_config_ok(cfg))) return rc;
     const uint8_t* blob = (const uint8_t*)packed_dev;
     const int T = cfg->n_frames;
     const int chunk = clip_chunk(cfg, B);

@@ -119,10 +119,12 @@ int ex_gemm(const float* A, int lda, const float* W, const float* bias, float* C
 // One CTA per (group, head): q, k, v [n x 16] in shared memory; thread = query row; two passes over the keys
 // (row maximum, then exp / sum / weighted values), softmax(q k^T * 16^-1/2) v like selfattention.py:18-41.
 // Group g: spatial (b, t) -> tokens g*17 + j; temporal (b, j) -> tokens (b*T + t)*17 + j.
+template <int DH>      // head_dim: 16 (8 heads) or 32 (4 heads, the reference constructor's default)
 __global__ void __launch_bounds__(128) ex_attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k,
                                                            const float* __restrict__ v, int ldkv, float* __restrict__ o,
                                                            int T, int temporal) {
     extern __shared__ float sm[];
+    const float scale = DH == 16 ? 0.25f : 0.17677669529663688110f;       // head_dim^-1/2 (selfattention.py:10)
     const int n = temporal ? T : J, h = blockIdx.y;
     const long long g = blockIdx.x;
     float *sq = sm, *sk = sm + n * DH, *sv = sm + 2 * n * DH;
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(128) ex_attention_kernel(const float* __restri
             float s = 0.f;
 #pragma unroll
             for (int c = 0; c < DH; ++c) s = fmaf(qi[c], sk[j * DH + c], s);
-            mx = fmaxf(mx, s * 0.25f);
+            mx = fmaxf(mx, s * scale);
         }
         float l = 0.f, acc[DH];
 #pragma unroll
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(128) ex_attention_kernel(const float* __restri
             float s = 0.f;
 #pragma unroll
             for (int c = 0; c < DH; ++c) s = fmaf(qi[c], sk[j * DH + c], s);
-            const float p = expf(s * 0.25f - mx);
+            const float p = expf(s * scale - mx);
             l += p;
 #pragma unroll
             for (int c = 0; c < DH; ++c) acc[c] = fmaf(p, sv[j * DH + c], acc[c]);
@@ -349,7 +351,13 @@ int exact_forward(const kasf_config* cfg, const float* image, const uint8_t* blo
                 }
                 const int n = temporal ? T : J;
                 const long long groups = temporal ? (long long)nb * J : (long long)nb * T;
-                ex_attention_kernel<<<dim3((unsigned)groups, HEADS), 128, (size_t)3 * n * DH * 4, st>>>(q, ldq, k, v, ldkv, w.T2, T, temporal);
+                if (cfg->num_heads == HEADS)
+                    ex_attention_kernel<16><<<dim3((unsigned)groups, 8), 128, (size_t)3 * n * 16 * 4, st>>>(q, ldq, k, v, ldkv, w.T2, T, temporal);
+                else {
+                    const size_t smem = (size_t)3 * n * 32 * 4;       // up to 93 KB at T = 243
+                    cudaFuncSetAttribute(ex_attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    ex_attention_kernel<32><<<dim3((unsigned)groups, 4), 128, smem, st>>>(q, ldq, k, v, ldkv, w.T2, T, temporal);
+                }
                 if ((r = cuda_status())) return r;
                 // out = in + ls1 * (o Wproj^T + bproj)
                 if ((r = ex_gemm<2>(w.T2, D, image + m.projw, image + m.projb, out, D, M, D, D, in, image + m.ls1, st))) return r;

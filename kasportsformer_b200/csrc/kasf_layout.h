@@ -21,12 +21,20 @@ constexpr int MAX_T = 243;
 
 inline int config_ok(const kasf_config* c) {
     if (!c) return KASF_EINVAL;
-    if (c->dim_feat != D || c->dim_rep != REP || c->num_heads != HEADS || c->mlp_ratio != 4 ||
+    // num_heads: 8 (every shipped YAML; the tensor-core kernels are specialised to 8 x 16) or 4 (the reference
+    // constructor's default, head_dim 32: KASF_PRECISION_EXACT only)
+    if (c->dim_feat != D || c->dim_rep != REP || (c->num_heads != HEADS && c->num_heads != 4) || c->mlp_ratio != 4 ||
         c->num_joints != J || c->neighbour_num != 4)
         return KASF_ESHAPE;
     if (c->n_layers < 1 || c->n_layers > 1024) return KASF_ESHAPE;
     if (c->n_frames < 4 || c->n_frames > MAX_T) return KASF_ESHAPE;
     return KASF_OK;
+}
+
+// the tensor-core ("fast") kernels
+inline int fast_config_ok(const kasf_config* c) {
+    const int rc = config_ok(c);
+    return rc ? rc : (c->num_heads == HEADS ? KASF_OK : KASF_ESHAPE);
 }
 
 static const int kLimbSize[17] = {3, 3, 2, 2, 3, 3, 4, 4, 4, 4, 3, 4, 4, 4, 4, 2, 2};

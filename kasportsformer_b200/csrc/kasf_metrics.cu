@@ -177,10 +177,15 @@ metrics_kernel(int T, const float* __restrict__ pred, const float* __restrict__ 
         const int t = (int)(fr % T);
         const double w = res[b * 2], h = res[b * 2 + 1];
         double p[17][3], g[17][3];
+        const int act = action ? action[b] : 0;
+        // an action index outside [0, n_actions) is a caller error: the clip is NOT accumulated (it must not corrupt
+        // another action's means); column 3 then sums to fewer than B * T frames, which finalize_metrics checks
+        if (act < 0 || act >= n_actions) {
+            if (per_frame) per_frame[fr * 3] = per_frame[fr * 3 + 1] = per_frame[fr * 3 + 2] = nan("");
+            continue;
+        }
         load_pred(pred, pflip, fr, w, h, factor[fr], p);
         load_gt(gt, fr, g);
-        int act = action ? action[b] : 0;
-        if (act < 0 || act >= n_actions) act = 0;
         double* row = acc + act * KASF_METRIC_COLS;
         double e1 = 0;
         for (int j = 0; j < 17; ++j) {

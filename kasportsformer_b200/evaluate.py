@@ -17,10 +17,14 @@ from . import _capi
 COLS = _capi.METRIC_COLS
 
 
-def finalize_metrics(sums: np.ndarray) -> Dict[str, object]:
+def finalize_metrics(sums: np.ndarray, expect_frames: Optional[int] = None) -> Dict[str, object]:
     """Per-action sums [A,22] -> the reference's result dict (train_and_evaluate_sp.py:105-127):
-    mean over frames per action, then mean over the actions that occurred."""
+    mean over frames per action, then mean over the actions that occurred.  expect_frames: the number of frames that
+    were fed; kasf_metrics skips clips whose action index is out of range, which shows up here as missing frames."""
     sums = np.asarray(sums, dtype=np.float64)
+    if expect_frames is not None and int(round(sums[:, 3].sum())) != int(expect_frames):
+        raise ValueError(f"{int(round(sums[:, 3].sum()))} frames accumulated, {expect_frames} expected: "
+                         "an action index was outside [0, n_actions)")
     seen = sums[:, 3] > 0
     s = sums[seen]
     mp = s[:, 0] / s[:, 3]

@@ -171,7 +171,9 @@ class KASportsFormer(nn.Module):
         self._pack_lock = threading.Lock()       # (shared with nn.DataParallel replicas: they copy __dict__ shallowly)
         # "fast": bf16 tensor-core operands (default) | "exact": the reference's fp32 arithmetic on CUDA cores,
         # an order of magnitude slower -- for checking a checkpoint's accuracy (README, "Precision")
-        self.precision = "fast"
+        # (num_heads = 4, head_dim 32 -- the reference constructor's default, used by no shipped YAML -- has no
+        #  tensor-core kernels: such a model runs in "exact" mode only)
+        self.precision = "fast" if int(num_heads) == 8 else "exact"
 
     # -- weight packing -------------------------------------------------------------------------
     def _signature(self):
@@ -226,10 +228,13 @@ class KASportsFormer(nn.Module):
         if self.precision not in ("fast", "exact"):
             raise ValueError(f'precision must be "fast" or "exact", got {self.precision!r}')
         exact = self.precision == "exact"
+        if not exact and self.cfg["num_heads"] != 8:
+            raise NotImplementedError('precision="fast" is built for num_heads=8 (head_dim 16); num_heads=4 runs with '
+                                      'precision="exact"')
         blob, img = self.packed_weights(x.device, with_image=True) if exact else (self.packed_weights(x.device), None)
         # the registered custom op (kasportsformer_b200/ops.py) -> ctypes -> kasf_forward_ex
         return torch.ops.kasf.forward(x, blob, img, self.cfg["n_layers"], self.cfg["n_frames"], bool(return_rep),
-                                      1 if exact else 0, 0)
+                                      1 if exact else 0, 0, self.cfg["num_heads"])
 
     def graphed(self, batch: int, return_rep: bool = False) -> "GraphedForward":
         """The forward for a fixed batch size captured once into a CUDA graph (the 186 launches of `kasf_forward`,

@@ -17,17 +17,17 @@ from . import _capi
 
 @torch.library.custom_op("kasf::forward", mutates_args=(), device_types="cuda")
 def kasf_forward(x: torch.Tensor, blob: torch.Tensor, image: Optional[torch.Tensor], n_layers: int, n_frames: int,
-                 return_rep: bool, precision: int, flags: int) -> torch.Tensor:
+                 return_rep: bool, precision: int, flags: int, num_heads: int = 8) -> torch.Tensor:
     """KASportsFormer.forward (reference model/KASportsFormer.py:320-347) -> kasf_forward_ex.
     x float32 [B, n_frames, 17, 3] contiguous; returns [B, n_frames, 17, 3] (or [.., 512] with return_rep)."""
-    cfg = dict(n_layers=n_layers, n_frames=n_frames, dim_feat=128, dim_rep=512, num_heads=8, mlp_ratio=4,
+    cfg = dict(n_layers=n_layers, n_frames=n_frames, dim_feat=128, dim_rep=512, num_heads=num_heads, mlp_ratio=4,
                num_joints=17, neighbour_num=4)
     return _capi.forward(cfg, blob, x, return_rep, precision="exact" if precision == 1 else "fast", image=image,
                          two_tiles=bool(flags & _capi.FLAG_TWO_TILES))
 
 
 @kasf_forward.register_fake
-def _(x, blob, image, n_layers, n_frames, return_rep, precision, flags):
+def _(x, blob, image, n_layers, n_frames, return_rep, precision, flags, num_heads=8):
     return x.new_empty(x.shape[0], x.shape[1], 17, 512 if return_rep else 3)
 
 

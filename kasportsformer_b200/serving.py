@@ -1,9 +1,15 @@
 """Variable-length serving front end: lift a whole video's 2D keypoints to 3D.
 
 Restates the clip handling of the reference demo (demo/demo.py:132-156 `resample` / `turn_into_clips`, :220-237 the
-per-clip loop, demo/lib/utils.py:5-19 `flip_data` / `normalize_screen_coordinates`) with one difference in
-execution, none in results: all clips of the video and their mirrored copies go through ONE forward as a
-[2 * n_clips, T, 17, 3] batch instead of two forwards per clip.
+per-clip loop, demo/lib/utils.py:5-19 `flip_data` / `normalize_screen_coordinates`) with two deliberate differences:
+
+* execution: all clips of the video and their mirrored copies go through ONE forward as a [2 * n_clips, T, 17, 3]
+  batch instead of two forwards per clip;
+* results: the test-time augmentation is the INTENDED one, (f(x) + flip(f(flip(x)))) / 2, as in the evaluation scripts
+  (train_and_evaluate_sp.py:46-51).  The demo as it actually runs differs: its `flip_data` (demo/lib/utils.py:5-13)
+  mutates its argument in place, so at demo.py:221-222 `input_2D` and `input_2D_aug` are the SAME flipped array and
+  the demo computes (f(flip(x)) + flip(f(flip(x)))) / 2.  That aliasing bug is not reproduced; pass
+  `reference_demo_aliasing=True` to `lift_video` to get the demo's literal behaviour (tests/test_gpu_io.py covers both).
 """
 from __future__ import annotations
 
@@ -53,13 +59,15 @@ def normalize_screen_coordinates(X: np.ndarray, w: float, h: float) -> np.ndarra
 
 @torch.no_grad()
 def lift_video(model, keypoints: np.ndarray, width: int, height: int, flip: bool = True, return_rep: bool = False,
-               max_batch: int = 4096) -> np.ndarray:
+               max_batch: int = 4096, reference_demo_aliasing: bool = False) -> np.ndarray:
     """2D keypoints of one video [n_frames, 17, 2|3] (pixels [, confidence]) -> root-relative 3D poses
     [n_frames, 17, 3] in the model's normalised units, following demo/demo.py:220-244: split into T-frame clips,
     flip test-time augmentation, average, un-stretch the last clip, zero the root joint.
 
     With return_rep=True returns the 512-d motion representation [n_frames, 17, 512] instead
-    (model/KASportsFormer.py:342-343; averaged over the two flips after mirroring the joints back)."""
+    (model/KASportsFormer.py:342-343; averaged over the two flips after mirroring the joints back).
+    reference_demo_aliasing: reproduce demo.py:221-233 literally -- its in-place `flip_data` makes BOTH forwards see
+    the flipped clip (module docstring); default False = the augmentation the evaluation scripts use."""
     kp = np.asarray(keypoints, np.float32)
     if kp.ndim != 3 or kp.shape[1] != 17 or kp.shape[2] not in (2, 3):
         raise ValueError("keypoints must be [n_frames, 17, 2|3]")
@@ -74,7 +82,8 @@ def lift_video(model, keypoints: np.ndarray, width: int, height: int, flip: bool
         xb = torch.from_numpy(x[i0:i0 + max_batch]).to(dev)
         n = xb.shape[0]
         if flip:
-            yy = model(torch.cat([xb, _capi.joint_flip(xb)], dim=0), return_rep=return_rep)
+            xf = _capi.joint_flip(xb)
+            yy = model(torch.cat([xf if reference_demo_aliasing else xb, xf], dim=0), return_rep=return_rep)
             y, yf = yy[:n], yy[n:]
             if return_rep:   # mirror the joints back; the representation has no x axis to negate
                 perm = torch.tensor(_capi.table(5), device=dev, dtype=torch.long)

@@ -50,10 +50,13 @@ def test_weight_image_matches_state_dict_schema(lib):
 
 
 def test_config_validation(lib):
-    bad = dict(CFG, num_heads=4)
+    bad = dict(CFG, num_heads=6)
     assert lib.kasf_weight_entries(C.byref(_capi.c_config(bad))) == -2
+    m4 = KASportsFormer()                      # the reference ctor's default num_heads=4 (no shipped YAML uses it)
+    assert m4.cfg["num_heads"] == 4 and m4.precision == "exact"      # ... runs in the fp32 path only
+    assert lib.kasf_weight_entries(C.byref(_capi.c_config(m4.cfg))) == lib.kasf_weight_entries(C.byref(_capi.c_config(CFG)))
     with pytest.raises(NotImplementedError):
-        KASportsFormer()                       # ctor default num_heads=4 is not a shipped config
+        KASportsFormer(num_heads=6)
     with pytest.raises(NotImplementedError):
         KASportsFormer(num_heads=8, hierarchical=True)
     with pytest.raises(NotImplementedError):

@@ -1,6 +1,7 @@
 """Rows f2 / f3 on the device: evaluation over a packed clip store through the pinned double-buffered feeder, and
 the variable-length serving front end against a per-clip restatement of the reference demo loop."""
 import numpy as np
+from conftest import load_golden
 import pytest
 import torch
 
@@ -66,3 +67,25 @@ def test_lift_video_matches_per_clip_demo_loop(n_frames):
     assert np.abs(out - ref).max() <= 1e-6 * max(1.0, np.abs(ref).max())
     rep = serving.lift_video(m, kp, 1920, 1080, flip=False, return_rep=True)
     assert rep.shape == (n_frames, 17, 512) and np.isfinite(rep).all()
+    # the demo as it actually runs: flip_data (demo/lib/utils.py:5-13) flips in place, so demo.py:232-233 feed the
+    # flipped clip to both forwards; reproduced only on request
+    z, _ = load_golden("serving.npz")
+    lit = serving.lift_video(m, kp, 1920, 1080, flip=True, reference_demo_aliasing=True)
+    ref2 = []
+    for i, c in enumerate(clips):
+        x = serving.normalize_screen_coordinates(c, 1920, 1080)
+        xa = x.copy()
+        xa[..., 0] *= -1                                   # flip_data, restated: negate x, swap left / right joints
+        xa[:, :, [1, 2, 3, 14, 15, 16] + [4, 5, 6, 11, 12, 13]] = xa[:, :, [4, 5, 6, 11, 12, 13] + [1, 2, 3, 14, 15, 16]]
+        x = xa                                             # the aliasing: `input_2D` IS `input_2D_aug` after the call
+        xt = torch.from_numpy(x).to(DEV)
+        y = (m(xt) + _capi.joint_flip(m(torch.from_numpy(xa).to(DEV)))) / 2
+        if i == len(clips) - 1 and down is not None:
+            y = y[:, torch.from_numpy(np.asarray(down, np.int64)).to(DEV)]
+        y[:, :, 0, :] = 0
+        ref2.append(y[0].cpu().numpy())
+    ref2 = np.concatenate(ref2, axis=0)
+    assert np.abs(lit - ref2).max() <= 1e-6 * max(1.0, np.abs(ref2).max())
+    assert np.abs(lit - out).max() > 1e-4                 # and it is a different result
+    x0 = z["flip_in"]
+    assert np.array_equal(_capi.joint_flip(torch.from_numpy(x0).to(DEV)).cpu().numpy(), z["flip_out"])

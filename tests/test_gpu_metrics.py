@@ -51,3 +51,21 @@ def test_metrics_large_batch_sums():
     assert abs(r["mpjpe"] - o["mpjpe"]) <= 1e-6 * o["mpjpe"]
     assert abs(r["p_mpjpe"] - o["p_mpjpe"]) <= 1e-6 * o["p_mpjpe"]
     assert abs(r["acceleration_error"] - o["accel"]) <= 1e-6 * o["accel"]
+
+
+def test_out_of_range_action_is_skipped_not_folded_into_action_0():
+    B, T = 6, 27
+    pred = synthetic.make_clips(B, T, 3, "gt") * 0.3
+    gt, factor, res, actions = synthetic.make_labels(B, T, 4, n_actions=3)
+    bad = actions.clone()
+    bad[1], bad[4] = 7, -1
+    good = _capi.metrics(pred.to(DEV), gt.to(DEV), res.to(DEV), factor.to(DEV), actions.to(DEV), 3).cpu().numpy()
+    got = _capi.metrics(pred.to(DEV), gt.to(DEV), res.to(DEV), factor.to(DEV), bad.to(DEV), 3).cpu().numpy()
+    keep = [i for i in range(B) if i not in (1, 4)]
+    want = _capi.metrics(pred[keep].to(DEV), gt[keep].to(DEV), res[keep].to(DEV), factor[keep].to(DEV),
+                         actions[keep].to(DEV), 3).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-12)
+    assert got[:, 3].sum() == (B - 2) * T and good[:, 3].sum() == B * T
+    with pytest.raises(ValueError):
+        finalize_metrics(got, expect_frames=B * T)
+    finalize_metrics(good, expect_frames=B * T)

@@ -100,3 +100,23 @@ def test_exact_mode_contract():
     assert m(x, return_rep=True).shape == (5, 27, 17, 512)
     m.precision = "fast"
     assert (m(x) - y).abs().max().item() < 5e-2
+
+
+def test_reference_ctor_default_num_heads_4_runs_exact_only():
+    """`KASportsFormer()` with the reference constructor's own default num_heads=4 (model/KASportsFormer.py:291-295; head_dim
+    32, no shipped YAML) constructs and runs -- in the fp32 path -- and matches the oracle; the tensor-core path refuses it."""
+    from oracle import kasf_oracle as O
+    cfg = dict(n_layers=2, n_frames=27, dim_feat=128, dim_rep=512, num_heads=4, mlp_ratio=4, num_joints=17,
+               neighbour_num=4)
+    state = synthetic.make_state(cfg, 12, "stress")
+    m = KASportsFormer(n_layers=2, n_frames=27)              # num_heads defaults to 4
+    m.load_state_dict(state)
+    m = m.to(DEV).eval()
+    assert m.precision == "exact"
+    x = synthetic.make_clips(3, 27, 6, "det")
+    y = m(x.to(DEV)).cpu()
+    ref = O.forward(state, x, O.default_config(n_layers=2, n_frames=27, num_heads=4))
+    assert (y - ref).abs().max().item() * MM <= 1e-2
+    m.precision = "fast"
+    with pytest.raises(NotImplementedError):
+        m(x.to(DEV))
