@@ -378,7 +378,7 @@ int exact_forward(const kasf_config* cfg, const float* image, const uint8_t* blo
             EX(launch_fusion(blob, l, w.A, w.G, w.Bn, w.X, M, st));
         }
         EX(launch_head(blob, w.X, y_dev ? y_dev + (size_t)b0 * T * J * 3 : nullptr,
-                       rep_dev ? rep_dev + (size_t)b0 * T * J * REP : nullptr, M, st));
+                       rep_dev ? rep_dev + (size_t)b0 * T * J * REP : nullptr, M, st, /*tensor_cores=*/false));
     }
 #undef EX
     return rc;

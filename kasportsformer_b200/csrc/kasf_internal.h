@@ -27,7 +27,9 @@ int pack_weights(const kasf_config* cfg, const float* image, void* packed, size_
 
 int launch_features(const uint8_t* blob, const float* x, float* bone, float* limb, float* X, float* XB, float* XL,
                     long long frames, cudaStream_t st);
-int launch_head(const uint8_t* blob, const float* X, float* y, float* rep, long long tokens, cudaStream_t st);
+// tensor_cores: head_tc_kernel (fp32-accurate bf16-triple MMAs); false: the fp32 FMA kernel (exact-precision path)
+int launch_head(const uint8_t* blob, const float* X, float* y, float* rep, long long tokens, cudaStream_t st,
+                bool tensor_cores = true);
 int launch_fusion(const uint8_t* blob, int layer, const float* a, const float* g, const float* b, float* out,
                   long long tokens, cudaStream_t st);
 // `scratch` (module_scratch_bytes(B, T) bytes, 256-byte aligned) is needed by temporal modules with T > 128 only

@@ -192,7 +192,17 @@ constexpr int G_REPB = G_REPW + D * REP;                   // [512]
 constexpr int G_HEADW = G_REPB + REP;                      // [3][512]
 constexpr int G_HEADB = G_HEADW + 3 * REP;                 // [3] (+pad)
 constexpr int G_FLOATS = G_HEADB + 4;
-constexpr size_t GLOBAL_BYTES = ((size_t)G_FLOATS * 4 + 1023) / 1024 * 1024;
+constexpr size_t GLOBAL_F_BYTES = ((size_t)G_FLOATS * 4 + 1023) / 1024 * 1024;
+// ... followed by rep_logit's weight as bf16 TRIPLES for the tensor-core head (kasf_head.cu): W = hi + mid + lo exactly
+// (3 x 8 mantissa bits), 8 pieces of 64 output columns, each piece = three [64 n x 128 k] operand images (hi | mid | lo,
+// 16 KB each: two K sub-tiles of [64 rows x 128 B], 128-byte swizzle) = 48 KB that one bulk copy lands MMA-ready
+constexpr size_t G_REP3_OFF = GLOBAL_F_BYTES;
+constexpr size_t REP3_IMG = 16384, REP3_PIECE = 3 * REP3_IMG;
+constexpr size_t GLOBAL_BYTES = GLOBAL_F_BYTES + 8 * REP3_PIECE;
+// byte offset of element (n, k) of a [64 x 128] image
+__host__ __device__ constexpr uint32_t img64_off(uint32_t n, uint32_t k) {
+    return (k >> 6) * 8192u + n * 128u + ((((k & 63u) >> 3) ^ (n & 7u)) << 4) + ((k & 7u) << 1);
+}
 
 inline size_t packed_bytes(const kasf_config* c) { return GLOBAL_BYTES + (size_t)c->n_layers * LAYER_BYTES; }
 __host__ __device__ inline size_t module_off(int layer, int mod) {

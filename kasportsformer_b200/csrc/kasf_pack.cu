@@ -202,6 +202,19 @@ __global__ void pack_global_kernel(const float* __restrict__ img, uint8_t* __res
         o[G_REPW + i] = img[g.repw + (size_t)n * D + k];
     }
     for (int i = tid; i < REP; i += nth) o[G_REPB + i] = img[g.repb + i];
+    // rep_logit's weight as bf16 triples (hi + mid + lo == the fp32 value): operand images of the tensor-core head
+    for (int i = tid; i < REP * D; i += nth) {
+        const int n = i / D, k = i % D;
+        const float w = img[g.repw + i];
+        const __nv_bfloat16 h = __float2bfloat16_rn(w);
+        const float r1 = w - __bfloat162float(h);
+        const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+        const __nv_bfloat16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+        uint8_t* piece = blob + G_REP3_OFF + (size_t)(n >> 6) * REP3_PIECE + img64_off(n & 63, k);
+        *reinterpret_cast<__nv_bfloat16*>(piece) = h;
+        *reinterpret_cast<__nv_bfloat16*>(piece + REP3_IMG) = m;
+        *reinterpret_cast<__nv_bfloat16*>(piece + 2 * REP3_IMG) = l;
+    }
     for (int i = tid; i < 3 * REP; i += nth) o[G_HEADW + i] = img[g.hw + i];
     for (int i = tid; i < 4; i += nth) o[G_HEADB + i] = i < 3 ? img[g.hb + i] : 0.f;
 }
