@@ -79,6 +79,9 @@ struct LayV1 {
 
 constexpr uint32_t TM_MIX = 0, TM_K = 128, TM_V = 256, TM_X = 384;   // mixer phase (Q lives at TM_MIX)
 constexpr uint32_t TM_H0 = 0, TM_H1 = 128, TM_OUT = 256;            // MLP phase
+// MLP phase: the two GELU output chunks as the fc2 A OPERAND IN TENSOR MEMORY (packed 16-bit pairs, lane = row, 64
+// columns per 128-wide chunk) in the columns the residual rows occupy during the mixer phase -- x1 stays in registers
+constexpr uint32_t TM_HS = 384;
 
 // mbarriers.  Ring: FULL (bulk-copy bytes) / EMPTY (tcgen05.commit).  Compute warps -> MMA warp: AREADY (the A
 // operand tile is written), HSREADY (hidden tile c written, hidden accumulator drained).  MMA warp -> compute
@@ -682,6 +685,34 @@ __device__ __forceinline__ void gather_rows(const ModParams& p, uint8_t* sm, int
     cp_async_mbar_arrive(bar);
 }
 
+// The same for the 16 rows that this warp's lane quarter and column half own: rows (warp & 3) * 32 + (warp >> 2) * 16 + k.
+// Arrives twice per lane (the barrier counts two half gathers per tile).
+template <int MODE>
+__device__ __forceinline__ void gather_rows_owned(const ModParams& p, uint8_t* sm, int tile, const float* src, uint64_t* bar,
+                                                  int warp, int lane) {
+    const int n = tile_rows<MODE>(p, tile);
+    const int r0 = (warp & 3) * 32 + (warp >> 2) * 16;
+    if (MODE == KASF_MODE_SPATIAL) {
+        const float* g = src + (long long)tile * 119 * D + lane * 4;
+#pragma unroll 4
+        for (int k = 0; k < 16; ++k) {
+            const int r = r0 + k;
+            if (r < n) cp_async16(sm + SM_STAGE + f32_off(r, lane), g + (size_t)r * D, 16u);
+        }
+    } else {
+        const int myrow = r0 + (lane & 15);
+        const int mytok = myrow < n ? (int)row_token<MODE>(p, tile, myrow) : 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int tok = __shfl_sync(0xffffffffu, mytok, k);
+            const int r = r0 + k;
+            if (r < n) cp_async16(sm + SM_STAGE + f32_off(r, lane), src + (size_t)tok * D + lane * 4, 16u);
+        }
+    }
+    cp_async_mbar_arrive(bar);
+    cp_async_mbar_arrive(bar);
+}
+
 // this thread's 64 staged values of its row (zeros for padding rows)
 __device__ __forceinline__ void read_staged(const uint8_t* sm, const EpiMap& e, float (&xv)[64], bool ok) {
     if (ok) {
@@ -787,13 +818,25 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
             }
         } else if (warp == W_MMA && lane == 0) {
             // ---- the only thread that issues tcgen05.mma
-            const uint32_t a0_addr = smem_u32(sm + SM_A0), a1_addr = smem_u32(sm + SM_A1), ring_addr = smem_u32(sm + SM_RING),
-                           hs_addr = smem_u32(sm + SM_HS);
+            const uint32_t a0_addr = smem_u32(sm + SM_A0), a1_addr = smem_u32(sm + SM_A1), ring_addr = smem_u32(sm + SM_RING);
             uint32_t cslot = 0, cph = 0, ph_a = 0, ph_hs0 = 0, ph_hs1 = 0, ph_limb = 0;
             auto chunk = [&](uint32_t tcol, uint32_t a_smem, bool acc, bool fp16_operands = false) {
                 mbar_wait(&bars[B_FULL0 + cslot], cph);
                 tc_fence_after();
                 umma_tile_k128(tmem + tcol, a_smem, ring_addr + cslot * CHUNK_BYTES, 128, acc, fp16_operands);
+                tc_commit(&bars[B_EMPTY0 + cslot]);
+                if (++cslot == RING) cslot = 0, cph ^= 1;
+            };
+            // fc2 chunk: A = GELU chunk in tensor memory (8 columns per K-step of 16), B = ring slot
+            auto chunk_ts = [&](uint32_t tcol, uint32_t a_tmem, bool acc) {
+                mbar_wait(&bars[B_FULL0 + cslot], cph);
+                tc_fence_after();
+                const uint32_t idesc = KASF_HALF_GELU ? umma_idesc_f16(128, 128) : umma_idesc_bf16(128, 128);
+                const uint64_t db = umma_desc_sw128(ring_addr + cslot * CHUNK_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    umma_ts(tmem + tcol, a_tmem + ks * 8, db + (uint64_t)(((ks >> 2) * 16384u + (ks & 3) * 32u) >> 4), idesc,
+                            (acc || ks > 0) ? 1u : 0u);
                 tc_commit(&bars[B_EMPTY0 + cslot]);
                 if (++cslot == RING) cslot = 0, cph ^= 1;
             };
@@ -858,7 +901,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                         tc_commit(&bars[buf ? B_HFULL1 : B_HFULL0]);
                         if (c == 1 && limb_tiles) tc_commit(&bars[B_A0FREE]);   // last reader of the A tile
                     }
-                    chunk(TM_OUT, hs_addr + buf * TILE_BYTES, c > 0, KASF_HALF_GELU != 0);   // fc2: fp16 x fp16
+                    chunk_ts(TM_OUT, tmem + TM_HS + buf * 64, c > 0);                          // fc2: fp16 x fp16
                     if (c < 3) tc_commit(&bars[buf ? B_HSFREE1 : B_HSFREE0]);   // (c == 2: B1 is free for the next tile's rows)
                     if (c == 3) tc_commit(&bars[B_OUT]);
                 }
@@ -895,6 +938,19 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
             const long long tok = row_ok ? row_token<MODE>(p, tile, e.row) : -1;
             float xv[64];
             float mean, rstd;
+            // The next tile's row gather, issued right after LN2 has been handed to the tensor cores -- where the warps
+            // would otherwise just wait for the first fc1 chunk -- instead of behind the last fc2 chunks.  The staging
+            // buffer (= K|V / z / the former shared-memory hidden tiles) is dead by then: the projection MMA, which this
+            // thread has seen complete, waited for the AREADY arrival of all eight warps, so every warp has left the mixer
+            // core, and the MLP no longer touches shared memory (its hidden activation lives in tensor memory).  Only a
+            // graph module still reads z in its mixer epilogue -- each thread its own row -- so a warp gathers exactly
+            // the rows that it and its partner warp (same rows, other column half) own, after meeting that partner.
+            auto next_rows = [&]() {
+                if (tile + (int)gridDim.x < p.ntiles) {
+                    if (KIND == KASF_KIND_GRAPH) pair_sync(e.warp);
+                    gather_rows_owned<MODE>(p, sm, tile + (int)gridDim.x, first_src, &bars[B_ROWS], warp, lane);
+                }
+            };
 
             if (KIND == KASF_KIND_BONE && !POST && !limb_tiles) {
                 // ---- K,V from the limb stream: LN_limb(XL) Wkv^T
@@ -1092,7 +1148,8 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 PMARK(8);
             }
 
-            // ---- x1 = x + ls1 * mixer  (TMEM -> registers -> TMEM), LN2 -> A operand
+            // ---- x1 = x + ls1 * mixer  (TMEM -> registers; x1 STAYS in registers until the output epilogue: its
+            //      tensor-memory columns hold the GELU chunks during the MLP), LN2 -> A operand
             {
                 // GCN: mix = relu(z + BN_node(acc + bU + rowsum*bV)); others: mix = acc + bproj
                 float bn_s = 1.f, bn_t = 0.f, rs = 0.f;
@@ -1129,17 +1186,14 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                         xv[b * 32 + c4 * 4 + 2] = fmaf(ls.z, m2, __uint_as_float(xr[c4 * 4 + 2]));
                         xv[b * 32 + c4 * 4 + 3] = fmaf(ls.w, m3, __uint_as_float(xr[c4 * 4 + 3]));
                     }
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) xr[i] = __float_as_uint(xv[b * 32 + i]);
-                    tmem_st32(e.tbase + TM_X + e.half * 64 + b * 32, xr);
                 }
             }
             PMARK(9);
             ln_stats(sm, e, xv, mean, rstd);
             ln_write<false, false>(sm, SM_A0, e, xv, mean, rstd, nullptr, nullptr, row_ok);
-            tmem_st_wait();
             warp_arrive(&bars[B_AREADY], lane);
             PMARK(10);
+            next_rows();
 
             // ---- MLP epilogues: hidden chunk c (fc1 accumulator in TMEM) -> 2*GELU -> 16-bit A operand tile AUX[c & 1]
             //      (requesting the next 32 accumulator columns while the current ones are computed was measured
@@ -1160,7 +1214,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 // two-stage software pipeline over groups of 8 columns: the tanh arguments of group g+1 are computed
                 // while the MUFU results of group g are in flight (the compiler's own schedule consumed each result
                 // a few instructions after issuing it: 1960 vs 1440 cycles per chunk, scripts/micro/gelu_epi.cu)
-                uint8_t* hs = sm + SM_HS + buf * TILE_BYTES;
+                uint32_t hsw[32];         // this thread's 64 hidden values of the chunk as 16-bit pairs: 32 TMEM columns
 #if KASF_HALF_GELU
                 const uint4* b1h = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(vec + V_B1H) + c * 128 + e.half * 64);
                 __half2 v[2][4], w[2][4];
@@ -1182,10 +1236,8 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
 #pragma unroll
                     for (int i = 0; i < 4; ++i) t[i] = tanh_h2(w[s2][i]);
                     if (g + 1 < 8) stage1(g + 1, s2 ^ 1);
-                    uint4 pk;
-                    pk.x = h2u(__hfma2(v[s2][0], t[0], v[s2][0])), pk.y = h2u(__hfma2(v[s2][1], t[1], v[s2][1]));
-                    pk.z = h2u(__hfma2(v[s2][2], t[2], v[s2][2])), pk.w = h2u(__hfma2(v[s2][3], t[3], v[s2][3]));
-                    *reinterpret_cast<uint4*>(hs + tile_off_bf16(e.row, e.half * 64 + g * 8)) = pk;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) hsw[g * 4 + i] = h2u(__hfma2(v[s2][i], t[i], v[s2][i]));
                 }
 #else
                 const float* b1 = vec + V_B1 + c * 128 + e.half * 64;
@@ -1209,28 +1261,21 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
 #pragma unroll
                     for (int i = 0; i < 8; ++i) t[i] = gelu2_tanh(w[s2][i]);
                     if (g + 1 < 8) stage1(g + 1, s2 ^ 1);
-                    uint4 pk;
-                    pk.x = pack_bf16(fmaf(v[s2][0], t[0], v[s2][0]), fmaf(v[s2][1], t[1], v[s2][1]));
-                    pk.y = pack_bf16(fmaf(v[s2][2], t[2], v[s2][2]), fmaf(v[s2][3], t[3], v[s2][3]));
-                    pk.z = pack_bf16(fmaf(v[s2][4], t[4], v[s2][4]), fmaf(v[s2][5], t[5], v[s2][5]));
-                    pk.w = pack_bf16(fmaf(v[s2][6], t[6], v[s2][6]), fmaf(v[s2][7], t[7], v[s2][7]));
-                    *reinterpret_cast<uint4*>(hs + tile_off_bf16(e.row, e.half * 64 + g * 8)) = pk;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) hsw[g * 4 + i] = pack_bf16(fmaf(v[s2][2 * i], t[2 * i], v[s2][2 * i]), fmaf(v[s2][2 * i + 1], t[2 * i + 1], v[s2][2 * i + 1]));
                 }
 #endif
+                // the chunk as the fc2 A operand in tensor memory: lane = row, column c = hidden (2c, 2c+1); one store
+                // instead of eight swizzled 16-byte shared-memory stores, and fc2 reads only its weights from shared memory
+                tmem_st32(e.tbase + TM_HS + buf * 64 + e.half * 32, hsw);
+                tmem_st_wait();
                 warp_arrive(&bars[buf ? B_HSREADY1 : B_HSREADY0], lane);
                 PMARK(11);
             }
-            // ---- B1 (hidden tile 0) was last read by fc2 of chunk 2: the first 64 rows of the next tile can be
-            //      requested a whole GELU epilogue + fc2 chunk earlier than the rest
-            wt.wait(B_HSFREE0);
-            if (tile + (int)gridDim.x < p.ntiles)
-                gather_rows<MODE>(p, sm, tile + (int)gridDim.x, first_src, &bars[B_ROWS], warp, lane, 0);
+            wt.wait(B_HSFREE0);                            // (fc2 of chunk 2: keeps the barrier's phases in step)
             wt.wait(B_OUT);
             tc_fence_after();
             PMARK(14);
-            // ---- B2 is free as well: request the other 64 rows; they land while the output epilogue runs
-            if (tile + (int)gridDim.x < p.ntiles)
-                gather_rows<MODE>(p, sm, tile + (int)gridDim.x, first_src, &bars[B_ROWS], warp, lane, 1);
             // ---- out = x1 + ls2 * (acc + b2): 256-bit stores of this thread's 64 columns, straight from registers
             //      (staging the rows in shared memory for coalesced 128-bit stores was measured slower: 4.4k vs 3.4k
             //       cycles per tile, the extra CTA barriers and the second pass over the data cost more than the LSU saves)
@@ -1238,10 +1283,10 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 float* orow = p.out + (tok >= 0 ? tok : 0) * D + e.half * 64;
 #pragma unroll
                 for (int b = 0; b < 2; ++b) {
-                    uint32_t acc[32], xr[32];
+                    uint32_t acc[32];
                     tmem_ld32(e.tbase + TM_OUT + e.half * 64 + b * 32, acc);
-                    tmem_ld32(e.tbase + TM_X + e.half * 64 + b * 32, xr);
                     tmem_ld_wait();
+                    const float* xr = xv + b * 32;         // x1, in registers since the mixer epilogue
 #pragma unroll
                     for (int c8 = 0; c8 < 4; ++c8) {
                         const int col = e.half * 64 + b * 32 + c8 * 8;
@@ -1251,10 +1296,10 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                             const float4 ls = *reinterpret_cast<const float4*>(vec + V_LS2 + col + h4 * 4);
                             const float4 b2 = *reinterpret_cast<const float4*>(vec + V_B2 + col + h4 * 4);
                             const int i = c8 * 8 + h4 * 4;
-                            o[h4 * 4 + 0] = fmaf(ls.x, __uint_as_float(acc[i + 0]) + b2.x, __uint_as_float(xr[i + 0]));
-                            o[h4 * 4 + 1] = fmaf(ls.y, __uint_as_float(acc[i + 1]) + b2.y, __uint_as_float(xr[i + 1]));
-                            o[h4 * 4 + 2] = fmaf(ls.z, __uint_as_float(acc[i + 2]) + b2.z, __uint_as_float(xr[i + 2]));
-                            o[h4 * 4 + 3] = fmaf(ls.w, __uint_as_float(acc[i + 3]) + b2.w, __uint_as_float(xr[i + 3]));
+                            o[h4 * 4 + 0] = fmaf(ls.x, __uint_as_float(acc[i + 0]) + b2.x, xr[i + 0]);
+                            o[h4 * 4 + 1] = fmaf(ls.y, __uint_as_float(acc[i + 1]) + b2.y, xr[i + 1]);
+                            o[h4 * 4 + 2] = fmaf(ls.z, __uint_as_float(acc[i + 2]) + b2.z, xr[i + 2]);
+                            o[h4 * 4 + 3] = fmaf(ls.w, __uint_as_float(acc[i + 3]) + b2.w, xr[i + 3]);
                         }
                         if (tok >= 0) stg256(orow + b * 32 + c8 * 8, o);
                     }
