@@ -62,7 +62,8 @@ constexpr uint32_t SM_A0 = SM_B0, SM_A1 = SM_B0;      // A operand tile (one buf
 constexpr uint32_t SM_RING = 98304 + KASF_RING_SHIFT;
 constexpr uint32_t SM_VEC = SM_RING + RING * 32768;
 constexpr uint32_t SM_PART = SM_VEC + (uint32_t)MOD_VEC_BYTES;   // float2 [128][2]
-constexpr uint32_t SM_ADJ = SM_PART + 2048;           // u32 [128][4]
+constexpr uint32_t SM_PART2 = SM_PART + 2048;         // second float2 [128][2]: ln_stats_merge alternates between the two
+constexpr uint32_t SM_ADJ = SM_PART2 + 2048;          // u32 [128][4]
 constexpr uint32_t SM_ROWSUM = SM_ADJ + 2048;         // f32 [128]
 constexpr uint32_t SM_RSD = SM_ROWSUM + 512;          // f32 [128]  degree^-1/2 of the temporal adjacency rows
 constexpr uint32_t SM_BARS = SM_RSD + 512;
@@ -249,6 +250,34 @@ __device__ __forceinline__ void ln_stats(uint8_t* sm, const EpiMap& e, const flo
     part[e.row * 2 + e.half].y = (q0 + q1) + (q2 + q3);
     pair_sync<L>(e.warp);
     const float var = (part[e.row * 2].y + part[e.row * 2 + 1].y) * (1.0f / D);
+    rstd = 1.0f / sqrtf(var + 1e-5f);
+}
+
+// The same statistics with ONE exchange between the two threads of a row instead of two: each half computes its own
+// mean and sum of squared deviations about a pivot (its first value: no cancellation), and the halves are merged with the
+// pairwise-variance formula  M2 = M2_a + M2_b + (mean_a - mean_b)^2 * n/2.  Same instruction count as the two-pass form,
+// one named barrier and one shared-memory round trip less per LayerNorm; agrees with it to fp32 rounding.  `flip`
+// alternates between two partial buffers (a thread may be one LayerNorm ahead of its partner's reads).
+__device__ __forceinline__ void ln_stats_merge(uint8_t* sm, const EpiMap& e, const float (&xv)[64], float& mean, float& rstd,
+                                               uint32_t& flip) {
+    float2* part = reinterpret_cast<float2*>(sm + (flip ? SM_PART2 : SM_PART));
+    flip ^= 1u;
+    const float pv = xv[0];
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 64; i += 4) {
+        const float d0 = xv[i] - pv, d1 = xv[i + 1] - pv, d2 = xv[i + 2] - pv, d3 = xv[i + 3] - pv;
+        s0 += d0, s1 += d1, s2 += d2, s3 += d3;
+        q0 = fmaf(d0, d0, q0), q1 = fmaf(d1, d1, q1), q2 = fmaf(d2, d2, q2), q3 = fmaf(d3, d3, q3);
+    }
+    const float s = (s0 + s1) + (s2 + s3), q = (q0 + q1) + (q2 + q3);
+    const float mh = fmaf(s, 1.0f / 64, pv), m2h = fmaf(-s * (1.0f / 64), s, q);
+    part[e.row * 2 + e.half] = make_float2(mh, m2h);
+    pair_sync(e.warp);
+    const float2 a = part[e.row * 2], b = part[e.row * 2 + 1];
+    const float dm = a.x - b.x;
+    mean = 0.5f * (a.x + b.x);
+    const float var = (a.y + b.y + 32.0f * dm * dm) * (1.0f / D);
     rstd = 1.0f / sqrtf(var + 1e-5f);
 }
 
@@ -917,6 +946,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
         e.warp = warp;
         e.tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         Waiter wt{smem_u32(bars), 0u};
+        uint32_t ln_flip = 0;
 
         long long pt0 = PROF ? clock64() : 0;
 #define PMARK(k)                                                      \
@@ -959,7 +989,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 csync();                                   // every limb row is in registers: the staging buffer
                 gather_rows<MODE>(p, sm, tile, p.in, &bars[B_ROWS], warp, lane, 0);   // receives the residual rows
                 gather_rows<MODE>(p, sm, tile, p.in, &bars[B_ROWS], warp, lane, 1);
-                ln_stats(sm, e, xv, mean, rstd);
+                ln_stats_merge(sm, e, xv, mean, rstd, ln_flip);
                 ln_write<false, false>(sm, SM_A1, e, xv, mean, rstd, nullptr, nullptr, row_ok);
                 warp_arrive(&bars[B_AREADY], lane);
                 PMARK(0);
@@ -984,7 +1014,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                     *reinterpret_cast<uint4*>(sm + SM_A0 + tile_off_bf16(e.row, e.half * 64 + c * 8)) = o8;
                 }
             } else {
-                ln_stats(sm, e, xv, mean, rstd);
+                ln_stats_merge(sm, e, xv, mean, rstd, ln_flip);
                 if (KIND == KASF_KIND_BONE) {
                     wt.wait(B_MMA);                            // K,V complete: the A tile may be overwritten
                     tc_fence_after();
@@ -1189,7 +1219,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 }
             }
             PMARK(9);
-            ln_stats(sm, e, xv, mean, rstd);
+            ln_stats_merge(sm, e, xv, mean, rstd, ln_flip);
             ln_write<false, false>(sm, SM_A0, e, xv, mean, rstd, nullptr, nullptr, row_ok);
             warp_arrive(&bars[B_AREADY], lane);
             PMARK(10);
