@@ -190,7 +190,8 @@ int kasf_former_module_ex(const kasf_config* cfg, const void* packed_dev, int la
  * spent in each phase of the kernel into phase_cycles_dev[24] (caller zeroes it): 0 limb K/V, 1 load+LN1,
  * 2 QKV MMA wait, 3 Q/K/V drain, 4 attention core, 5 projection MMA wait, 6 similarity/top-k, 7 aggregation,
  * 8 V MMA wait, 9 mixer epilogue, 10 LN2, 11 MLP epilogue compute, 12 output epilogue, 13 wait for the gathered
- * rows, 14 MLP waits for MMAs, 15 MLP tensor-memory loads (16..23 spare). */
+ * rows, 14 MLP waits for MMAs inside the chunk loop, 15 MLP tensor-memory loads, 16 wait for the last fc2 chunk,
+ * 17 wait for the first fc1 chunk (18..23 spare). */
 int kasf_former_module_profiled(const kasf_config* cfg, const void* packed_dev, int layer, int kind,
                                 int mode, const float* in_dev, const float* XL_dev, float* out_dev,
                                 int B, void* stream, unsigned long long* phase_cycles_dev);

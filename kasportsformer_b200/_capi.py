@@ -391,7 +391,7 @@ def former_module(cfg, blob, layer, kind, mode, v, XL=None, out=None, use_limb_t
 
 PHASES = ["limb_kv", "load_ln1", "qkv_mma_wait", "qkv_drain", "attention", "proj_mma_wait", "similarity",
           "aggregation", "v_mma_wait", "mixer_epilogue", "ln2", "mlp", "out_epilogue", "rows_wait",
-          "mlp_wait", "mlp_tmem_ld"]
+          "mlp_wait", "mlp_tmem_ld", "last_fc2_wait", "first_fc1_wait"]
 
 
 def former_module_phases(cfg, blob, layer, kind, mode, v, XL=None):

@@ -1235,7 +1235,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 wt.wait(buf ? B_HFULL1 : B_HFULL0);
                 tc_fence_after();
                 if (c >= 2) { wt.wait(buf ? B_HSFREE1 : B_HSFREE0); }
-                PMARK(14);
+                PMARK(c == 0 ? 17 : 14);
                 uint32_t acc[2][32];
                 tmem_ld32(e.tbase + (buf ? TM_H1 : TM_H0) + e.half * 64, acc[0]);
                 tmem_ld32(e.tbase + (buf ? TM_H1 : TM_H0) + e.half * 64 + 32, acc[1]);
@@ -1302,10 +1302,13 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 warp_arrive(&bars[buf ? B_HSREADY1 : B_HSREADY0], lane);
                 PMARK(11);
             }
+            // (reading the next tile's staged rows and taking their LN1 statistics here, under the last fc2 chunks, was
+            //  measured slower -- 13.2k vs 13.9k clips/s: 64 more live registers through the out epilogue cost more
+            //  than the ~0.9k cycles of wait they fill)
             wt.wait(B_HSFREE0);                            // (fc2 of chunk 2: keeps the barrier's phases in step)
             wt.wait(B_OUT);
             tc_fence_after();
-            PMARK(14);
+            PMARK(16);
             // ---- out = x1 + ls2 * (acc + b2): 256-bit stores of this thread's 64 columns, straight from registers
             //      (staging the rows in shared memory for coalesced 128-bit stores was measured slower: 4.4k vs 3.4k
             //       cycles per tile, the extra CTA barriers and the second pass over the data cost more than the LSU saves)
