@@ -160,8 +160,8 @@ int kasf_forward_launches(const kasf_config* cfg, int B) {
     const int chunk = clip_chunk(cfg, B);
     const int passes = (B + chunk - 1) / chunk;
     // T > 128: a temporal module is 3 kernels (attention, bone) or 2 (graph) instead of 1
-    const int per_layer = cfg->n_frames > 128 ? 7 + 2 + 1 + 2 : 7;
-    const int limb = cfg->n_frames > 128 ? 1 : 2;   // limb_tiles_kernel launches
+    const int per_layer = cfg->n_frames > KASF_SPLIT_T ? 7 + 2 + 1 + 2 : 7;
+    const int limb = cfg->n_frames > KASF_SPLIT_T ? 1 : 2;   // limb_tiles_kernel launches
     return passes * (1 + limb + cfg->n_layers * per_layer + 1);
 }
 

@@ -7,6 +7,13 @@
 #include "kasf_ptx.cuh"
 #include "kasf_tables.cuh"
 
+// Temporal modules of sequences longer than this many frames take the split path (projection kernel, per-sequence
+// mixer-core kernel, dense 128-row tail tiles) instead of the fused one-kernel path, which can only own whole
+// sequences per 128-row tile.
+#ifndef KASF_SPLIT_T
+#define KASF_SPLIT_T 64
+#endif
+
 namespace kasf {
 
 // CUDA launch status -> C-ABI code

@@ -1498,19 +1498,23 @@ __global__ void __launch_bounds__(256, 1) long_pre_kernel(const ModParams p) {
 // ---- attention core of one (clip, joint) sequence, T <= 256: Q | K | V bf16 [256 x 128] resident in shared
 //      memory (rows >= T zero), warp = head, 16-query blocks, two passes over the keys (row maximum, then
 //      probabilities and P V) so that the rounding is the one of the fused kernel; the output replaces Q.
-constexpr uint32_t LA_TILE = 256 * 256;   // one [256 rows x 128 bf16] tile
+//      The tiles hold the sequence padded to whole 64-key blocks (la_rows), so sequences of up to 128 frames take
+//      half the shared memory and two CTAs share an SM (MINB = 2).
+__host__ __device__ constexpr uint32_t la_rows(int T) { return (uint32_t)((T + 63) & ~63); }
 __device__ __forceinline__ uint32_t la_off(uint32_t r, uint32_t c16) { return r * 256u + ((c16 ^ (r & 7u)) << 4); }
 
-__global__ void __launch_bounds__(256, 1) long_attention_kernel(const ModParams p) {
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) long_attention_kernel(const ModParams p) {
     extern __shared__ __align__(1024) uint8_t sm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, T = p.T;
     const long long seq = blockIdx.x;
     __nv_bfloat16* gq = p.sq + seq * T * D;
     const __nv_bfloat16* gk = p.sk + seq * T * D;
     const __nv_bfloat16* gv = p.sv + seq * T * D;
+    const uint32_t rows = la_rows(T), LA_TILE = rows * 256u;   // one [rows x 128 bf16] tile
     // ---- load (16-byte chunks, coalesced), zero the tail rows
-    for (int i = tid; i < 3 * 256 * 16; i += 256) {
-        const int m = i / (256 * 16), r = (i / 16) & 255, c = i & 15;
+    for (uint32_t i = tid; i < 3 * rows * 16; i += 256) {
+        const uint32_t m = i / (rows * 16), r = (i >> 4) % rows, c = i & 15;
         uint8_t* dst = sm + m * LA_TILE + la_off(r, c);
         if (r < T) {
             const __nv_bfloat16* src = (m == 0 ? gq : (m == 1 ? gk : gv)) + (size_t)r * D + c * 8;
@@ -1809,8 +1813,10 @@ __global__ void __launch_bounds__(256, 1) long_gcn_kernel(const ModParams p) {
     }
 }
 
+#include "kasf_long_gcn.cuh"
+
 size_t module_scratch_bytes(int B, int T) {
-    if (T <= 128 || B <= 0) return 0;
+    if (T <= KASF_SPLIT_T || B <= 0) return 0;
     const size_t rows = (size_t)B * J * T;
     return 3 * rows * D * 2 + ((rows * 4 + 255) / 256) * 256;
 }
@@ -1828,9 +1834,7 @@ static int launch_long(ModParams p, int kind, void* scratch, size_t scratch_byte
     const int seqs = p.B * J;
     int rc;
     if (kind == KASF_KIND_GRAPH) {
-        cudaFuncSetAttribute(long_gcn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LG_TOTAL);
-        long_gcn_kernel<<<seqs, 256, LG_TOTAL, st>>>(p);
-        if ((rc = cuda_status())) return rc;
+        if ((rc = p.T <= 128 ? lgt::launch_gcn_tc<1>(p, seqs, st) : lgt::launch_gcn_tc<2>(p, seqs, st))) return rc;
         return launch_one<KASF_KIND_GRAPH, KASF_MODE_LONG, 0>(p, st);
     }
     if (kind == KASF_KIND_ATTENTION) {
@@ -1841,8 +1845,14 @@ static int launch_long(ModParams p, int kind, void* scratch, size_t scratch_byte
         long_pre_kernel<KASF_KIND_BONE><<<p.ntiles, 256, SM_TOTAL, st>>>(p);
     }
     if ((rc = cuda_status())) return rc;
-    cudaFuncSetAttribute(long_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * LA_TILE);
-    long_attention_kernel<<<seqs, 256, 3 * LA_TILE, st>>>(p);
+    const int la_bytes = 3 * (int)la_rows(p.T) * 256;
+    if (p.T <= 128) {
+        cudaFuncSetAttribute(long_attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, la_bytes);
+        long_attention_kernel<2><<<seqs, 256, la_bytes, st>>>(p);
+    } else {
+        cudaFuncSetAttribute(long_attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, la_bytes);
+        long_attention_kernel<1><<<seqs, 256, la_bytes, st>>>(p);
+    }
     if ((rc = cuda_status())) return rc;
     return kind == KASF_KIND_ATTENTION ? launch_one<KASF_KIND_ATTENTION, KASF_MODE_LONG, 0>(p, st)
                                        : launch_one<KASF_KIND_BONE, KASF_MODE_LONG, 0>(p, st);
@@ -1894,7 +1904,7 @@ static void mode_tiling(ModParams& p, int mode) {
 }
 
 size_t limb_tiles_bytes(int B, int T, int mode) {
-    if (mode == KASF_MODE_TEMPORAL && T > 128) return 0;   // split path: the projection kernel reads the fp32 rows
+    if (mode == KASF_MODE_TEMPORAL && T > KASF_SPLIT_T) return 0;   // split path: the projection kernel reads the fp32 rows
     ModParams p;
     p.B = B, p.T = T;
     mode_tiling(p, mode);
@@ -1936,7 +1946,7 @@ int launch_former_module(const uint8_t* blob, int layer, int kind, int mode, con
     p.srow = nullptr;
     p.xlt = kind == KASF_KIND_BONE ? static_cast<const uint8_t*>(limb_tiles) : nullptr;
     if (((uintptr_t)p.xlt & 127) != 0) return KASF_EINVAL;
-    if (mode == KASF_MODE_TEMPORAL && T > 128)
+    if (mode == KASF_MODE_TEMPORAL && T > KASF_SPLIT_T)
         return (flags & KASF_FLAG_TWO_TILES) ? KASF_ESHAPE : launch_long(p, kind, scratch, scratch_bytes, st);
     int tc = 0;
     if (mode == KASF_MODE_SPATIAL) {
