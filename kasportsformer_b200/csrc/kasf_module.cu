@@ -1378,25 +1378,44 @@ static int launch_one(const ModParams& p, cudaStream_t st) {
 //                      former_module_kernel<GRAPH, KASF_MODE_LONG> (U z + (A_hat z) V^T, BN, residuals, MLP)
 // Same arithmetic as the fused kernels (bf16 operands, fp32 accumulation / statistics / softmax / similarity).
 
-// ---- Q, K, V projection of 128 consecutive (sequence, frame) rows.  One CTA per tile, 8 warps, thread = half a
-//      row; the three weight chunks land in the ring region with one bulk copy each.
+// ---- Q, K, V projection of 128 consecutive (sequence, frame) rows.  Persistent: one CTA per SM walks the tiles
+//      with the three weight chunks (96 KB), the vector block, the barriers and the tensor-memory allocation set
+//      up once; 8 warps, thread = half a row.  The fp32 rows of the NEXT tile are gathered with cp.async into the
+//      staging buffer while the MMAs of the current tile run and its accumulators are drained (256-bit stores: one
+//      full sector per thread and instruction), and each of Q, K, V is drained as soon as its own MMAs complete.
+//      A bone module takes the limb operand of a tile ready-made (limb_tiles_kernel<LONG>: one 32 KB bulk copy
+//      straight into the A tile, requested as soon as the tile's last MMA has read the previous operand); without
+//      limb tiles it normalises the fp32 limb rows itself.
+//      (The first version was one CTA per tile and paid the 96 KB weight load, the allocation and every latency in
+//      series: 23.7k cycles per tile at T = 81, more than the tail kernel's whole MLP.)
 template <int KIND>
 __global__ void __launch_bounds__(256, 1) long_pre_kernel(const ModParams p) {
     extern __shared__ __align__(1024) uint8_t sm[];
+    enum { BW = 0, BR = 1, BL = 2, BQ = 3, BK = 4, BV = 5 };
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SM_BARS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + SM_BARS + 64);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, tile = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float* vec = reinterpret_cast<const float*>(sm + SM_VEC);
     const uint8_t* chunks = p.mod + MOD_VEC_BYTES;
+    const bool lt = KIND == KASF_KIND_BONE && p.xlt != nullptr;
+    const float* first_src = (KIND == KASF_KIND_BONE && !lt) ? p.xl : p.in;
     if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+        mbar_init(&bars[BW], 1);
+        mbar_init(&bars[BR], 512);                         // every lane, once per 64-row part
+        mbar_init(&bars[BL], 1);
+        mbar_init(&bars[BQ], 1);
+        mbar_init(&bars[BK], 1);
+        mbar_init(&bars[BV], 1);
         fence_mbar_init();
         // ring slot i <- chunk ORD[i]: attention Q,K,V = 0,1,2; bone K,V,Q = 1,2,0
-        mbar_arrive_expect_tx(&bars[0], 3 * CHUNK_BYTES);
+        mbar_arrive_expect_tx(&bars[BW], 3 * CHUNK_BYTES);
         for (int i = 0; i < 3; ++i) {
             const int ci = KIND == KASF_KIND_ATTENTION ? i : (i + 1) % 3;
-            bulk_g2s(sm + SM_RING + i * CHUNK_BYTES, chunks + (size_t)ci * CHUNK_BYTES, CHUNK_BYTES, &bars[0]);
+            bulk_g2s(sm + SM_RING + i * CHUNK_BYTES, chunks + (size_t)ci * CHUNK_BYTES, CHUNK_BYTES, &bars[BW]);
+        }
+        if (lt) {
+            mbar_arrive_expect_tx(&bars[BL], TILE_BYTES);
+            bulk_g2s(sm + SM_A0, p.xlt + (size_t)blockIdx.x * TILE_BYTES, TILE_BYTES, &bars[BL]);
         }
     }
     if (warp == 0) {
@@ -1407,88 +1426,129 @@ __global__ void __launch_bounds__(256, 1) long_pre_kernel(const ModParams p) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    gather_rows<KASF_MODE_LONG>(p, sm, blockIdx.x, first_src, &bars[BR], warp, lane, 0);
+    gather_rows<KASF_MODE_LONG>(p, sm, blockIdx.x, first_src, &bars[BR], warp, lane, 1);
     const uint32_t tmem = *tmem_slot;
     EpiMap e;
     e.row = (warp & 3) * 32 + lane, e.half = warp >> 2, e.warp = warp;
     e.tbase = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const int nrows = tile_rows<KASF_MODE_LONG>(p, tile);
-    const bool row_ok = e.row < nrows;
-    const long long tok = row_ok ? row_token<KASF_MODE_LONG>(p, tile, e.row) : 0;
     const uint32_t a_addr = smem_u32(sm + SM_A0), ring = smem_u32(sm + SM_RING);
     float xv[64], mean, rstd;
-    auto load_row = [&](const float* src) {
-        if (row_ok) {
+    uint32_t ph_r = 0, ph_l = 0, ph_m = 0;
+    if (tid == 0) mbar_wait(&bars[BW], 0);                 // weights resident (the issuing thread is their only reader)
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const bool row_ok = e.row < tile_rows<KASF_MODE_LONG>(p, tile);
+        const int next = tile + (int)gridDim.x;
+        const long long R = (long long)tile * 128 + e.row;
+        auto drain = [&](int qkv) {
+            __nv_bfloat16* dst = (qkv == 0 ? p.sq : (qkv == 1 ? p.sk : p.sv)) + R * D + e.half * 64;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) ldg256(src + tok * D + e.half * 64 + c * 8, xv + c * 8);
-        } else {
+            for (int b = 0; b < 2; ++b) {
+                uint32_t acc[32];
+                tmem_ld32(e.tbase + qkv * 128 + e.half * 64 + b * 32, acc);
+                tmem_ld_wait();
+                if (qkv == 0) {                                // query bias W_q beta_1
 #pragma unroll
-            for (int i = 0; i < 64; ++i) xv[i] = 0.f;
-        }
-    };
-    uint32_t ph = 0;
-    if (KIND == KASF_KIND_BONE) {
-        load_row(p.xl);
-        ln_stats(sm, e, xv, mean, rstd);
-        ln_write<false, false>(sm, SM_A0, e, xv, mean, rstd, nullptr, nullptr, row_ok);
-        fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
-            mbar_wait(&bars[0], 0);
-            tc_fence_after();
-            umma_tile_k128(tmem + TM_K, a_addr, ring, 128, false);
-            umma_tile_k128(tmem + TM_V, a_addr, ring + CHUNK_BYTES, 128, false);
-            tc_commit(&bars[1]);
-        }
-        mbar_wait(&bars[1], ph);
-        ph ^= 1;
-        tc_fence_after();
-    }
-    load_row(p.in);
-    ln_stats(sm, e, xv, mean, rstd);
-    ln_write<false, false>(sm, SM_A0, e, xv, mean, rstd, nullptr, nullptr, row_ok);
-    fence_proxy_async();
-    __syncthreads();
-    if (tid == 0) {
-        mbar_wait(&bars[0], 0);
-        tc_fence_after();
-        if (KIND == KASF_KIND_ATTENTION) {
-            umma_tile_k128(tmem + TM_MIX, a_addr, ring, 128, false);
-            umma_tile_k128(tmem + TM_K, a_addr, ring + CHUNK_BYTES, 128, false);
-            umma_tile_k128(tmem + TM_V, a_addr, ring + 2 * CHUNK_BYTES, 128, false);
-        } else {
-            umma_tile_k128(tmem + TM_MIX, a_addr, ring + 2 * CHUNK_BYTES, 128, false);
-        }
-        tc_commit(&bars[1]);
-    }
-    mbar_wait(&bars[1], ph);
-    tc_fence_after();
-    // ---- drain: bf16 rows of Q, K, V -> scratch (128 contiguous bytes per thread and matrix)
-    const long long R = (long long)tile * 128 + e.row;
+                    for (int i = 0; i < 32; ++i)
+                        acc[i] = __float_as_uint(__uint_as_float(acc[i]) + vec[V_BQ + e.half * 64 + b * 32 + i]);
+                }
+                if (row_ok) {
 #pragma unroll
-    for (int qkv = 0; qkv < 3; ++qkv) {
-        __nv_bfloat16* dst = (qkv == 0 ? p.sq : (qkv == 1 ? p.sk : p.sv)) + R * D + e.half * 64;
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t w[8];
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-            uint32_t acc[32];
-            tmem_ld32(e.tbase + qkv * 128 + e.half * 64 + b * 32, acc);
-            tmem_ld_wait();
-            if (qkv == 0) {                                // query bias W_q beta_1
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    acc[i] = __float_as_uint(__uint_as_float(acc[i]) + vec[V_BQ + e.half * 64 + b * 32 + i]);
-            }
-            if (row_ok) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint4 pk;
-                    pk.x = pack_bf16(__uint_as_float(acc[c * 8 + 0]), __uint_as_float(acc[c * 8 + 1]));
-                    pk.y = pack_bf16(__uint_as_float(acc[c * 8 + 2]), __uint_as_float(acc[c * 8 + 3]));
-                    pk.z = pack_bf16(__uint_as_float(acc[c * 8 + 4]), __uint_as_float(acc[c * 8 + 5]));
-                    pk.w = pack_bf16(__uint_as_float(acc[c * 8 + 6]), __uint_as_float(acc[c * 8 + 7]));
-                    *reinterpret_cast<uint4*>(dst + b * 32 + c * 8) = pk;
+                        for (int i = 0; i < 8; ++i)
+                            w[i] = pack_bf16(__uint_as_float(acc[c * 16 + 2 * i]), __uint_as_float(acc[c * 16 + 2 * i + 1]));
+                        stg256u(dst + b * 32 + c * 16, w);
+                    }
                 }
             }
+        };
+        if (KIND == KASF_KIND_BONE) {
+            if (lt) {
+                tc_fence_before();
+                __syncthreads();                           // every thread has drained K, V of the previous tile
+                if (tid == 0) {
+                    mbar_wait(&bars[BL], ph_l);
+                    tc_fence_after();
+                    umma_tile_k128(tmem + TM_K, a_addr, ring, 128, false);
+                    tc_commit(&bars[BK]);
+                    umma_tile_k128(tmem + TM_V, a_addr, ring + CHUNK_BYTES, 128, false);
+                    tc_commit(&bars[BV]);
+                }
+                ph_l ^= 1;
+            } else {
+                mbar_wait(&bars[BR], ph_r);
+                ph_r ^= 1;
+                read_staged(sm, e, xv, row_ok);
+                ln_stats(sm, e, xv, mean, rstd);
+                ln_write<false, false>(sm, SM_A0, e, xv, mean, rstd, nullptr, nullptr, row_ok);
+                fence_proxy_async();
+                tc_fence_before();
+                __syncthreads();
+                if (tid == 0) {
+                    tc_fence_after();
+                    umma_tile_k128(tmem + TM_K, a_addr, ring, 128, false);
+                    tc_commit(&bars[BK]);
+                    umma_tile_k128(tmem + TM_V, a_addr, ring + CHUNK_BYTES, 128, false);
+                    tc_commit(&bars[BV]);
+                }
+                gather_rows<KASF_MODE_LONG>(p, sm, tile, p.in, &bars[BR], warp, lane, 0);
+                gather_rows<KASF_MODE_LONG>(p, sm, tile, p.in, &bars[BR], warp, lane, 1);
+            }
         }
+        mbar_wait(&bars[BR], ph_r);
+        ph_r ^= 1;
+        read_staged(sm, e, xv, row_ok);
+        ln_stats(sm, e, xv, mean, rstd);
+        if (KIND == KASF_KIND_BONE) {
+            mbar_wait(&bars[BV], ph_m);                    // K, V MMAs (committed in this order) have read the limb operand
+            tc_fence_after();
+        }
+        ln_write<false, false>(sm, SM_A0, e, xv, mean, rstd, nullptr, nullptr, row_ok);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            if (KIND == KASF_KIND_ATTENTION) {
+                umma_tile_k128(tmem + TM_MIX, a_addr, ring, 128, false);
+                tc_commit(&bars[BQ]);
+                umma_tile_k128(tmem + TM_K, a_addr, ring + CHUNK_BYTES, 128, false);
+                tc_commit(&bars[BK]);
+                umma_tile_k128(tmem + TM_V, a_addr, ring + 2 * CHUNK_BYTES, 128, false);
+                tc_commit(&bars[BV]);
+            } else {
+                umma_tile_k128(tmem + TM_MIX, a_addr, ring + 2 * CHUNK_BYTES, 128, false);
+                tc_commit(&bars[BQ]);
+            }
+        }
+        if (next < p.ntiles) {                              // staging is free: every thread has its rows in registers
+            gather_rows<KASF_MODE_LONG>(p, sm, next, first_src, &bars[BR], warp, lane, 0);
+            gather_rows<KASF_MODE_LONG>(p, sm, next, first_src, &bars[BR], warp, lane, 1);
+        }
+        if (KIND == KASF_KIND_BONE) {
+            drain(1);
+            drain(2);
+            mbar_wait(&bars[BQ], ph_m);
+            tc_fence_after();
+            if (lt && tid == 0 && next < p.ntiles) {        // the A tile is free: next tile's limb operand
+                mbar_arrive_expect_tx(&bars[BL], TILE_BYTES);
+                bulk_g2s(sm + SM_A0, p.xlt + (size_t)next * TILE_BYTES, TILE_BYTES, &bars[BL]);
+            }
+            drain(0);
+        } else {
+            mbar_wait(&bars[BQ], ph_m);
+            tc_fence_after();
+            drain(0);
+            mbar_wait(&bars[BK], ph_m);
+            tc_fence_after();
+            drain(1);
+            mbar_wait(&bars[BV], ph_m);
+            tc_fence_after();
+            drain(2);
+        }
+        ph_m ^= 1;
     }
     tc_fence_before();
     __syncthreads();
@@ -1837,12 +1897,13 @@ static int launch_long(ModParams p, int kind, void* scratch, size_t scratch_byte
         if ((rc = p.T <= 128 ? lgt::launch_gcn_tc<1>(p, seqs, st) : lgt::launch_gcn_tc<2>(p, seqs, st))) return rc;
         return launch_one<KASF_KIND_GRAPH, KASF_MODE_LONG, 0>(p, st);
     }
+    const int pre_grid = p.ntiles < sm_count() ? p.ntiles : sm_count();
     if (kind == KASF_KIND_ATTENTION) {
         cudaFuncSetAttribute(long_pre_kernel<KASF_KIND_ATTENTION>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
-        long_pre_kernel<KASF_KIND_ATTENTION><<<p.ntiles, 256, SM_TOTAL, st>>>(p);
+        long_pre_kernel<KASF_KIND_ATTENTION><<<pre_grid, 256, SM_TOTAL, st>>>(p);
     } else {
         cudaFuncSetAttribute(long_pre_kernel<KASF_KIND_BONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
-        long_pre_kernel<KASF_KIND_BONE><<<p.ntiles, 256, SM_TOTAL, st>>>(p);
+        long_pre_kernel<KASF_KIND_BONE><<<pre_grid, 256, SM_TOTAL, st>>>(p);
     }
     if ((rc = cuda_status())) return rc;
     const int la_bytes = 3 * (int)la_rows(p.T) * 256;
@@ -1897,6 +1958,9 @@ static void mode_tiling(ModParams& p, int mode) {
     if (mode == KASF_MODE_SPATIAL) {
         p.groups_per_tile = 7;
         p.ntiles = (int)(((long long)p.B * p.T + 6) / 7);
+    } else if (p.T > KASF_SPLIT_T) {                       // split path: 128 consecutive (sequence, frame) rows
+        p.groups_per_tile = 0;
+        p.ntiles = (int)(((long long)p.B * J * p.T + 127) / 128);
     } else {
         p.groups_per_tile = 128 / p.T;
         p.ntiles = (int)(((long long)p.B * J + p.groups_per_tile - 1) / p.groups_per_tile);
@@ -1904,7 +1968,6 @@ static void mode_tiling(ModParams& p, int mode) {
 }
 
 size_t limb_tiles_bytes(int B, int T, int mode) {
-    if (mode == KASF_MODE_TEMPORAL && T > KASF_SPLIT_T) return 0;   // split path: the projection kernel reads the fp32 rows
     ModParams p;
     p.B = B, p.T = T;
     mode_tiling(p, mode);
@@ -1921,6 +1984,7 @@ int launch_limb_tiles(const float* XL, void* tiles, int B, int T, int mode, cuda
     mode_tiling(p, mode);
     const int grid = p.ntiles < sm_count() * 8 ? p.ntiles : sm_count() * 8;
     if (mode == KASF_MODE_SPATIAL) limb_tiles_kernel<KASF_MODE_SPATIAL><<<grid, 256, 0, st>>>(p, static_cast<uint8_t*>(tiles));
+    else if (T > KASF_SPLIT_T) limb_tiles_kernel<KASF_MODE_LONG><<<grid, 256, 0, st>>>(p, static_cast<uint8_t*>(tiles));
     else limb_tiles_kernel<KASF_MODE_TEMPORAL><<<grid, 256, 0, st>>>(p, static_cast<uint8_t*>(tiles));
     return cuda_status();
 }
