@@ -234,8 +234,17 @@ int kasf_former_module_profiled(const kasf_config* cfg, const void* packed_dev, 
     if (!packed_dev || !in_dev || !out_dev || !phase_cycles_dev || B < 0 || layer < 0 || layer >= cfg->n_layers)
         return KASF_EINVAL;
     if ((rc = device_ok())) return rc;
-    return launch_former_module((const uint8_t*)packed_dev, layer, kind, mode, in_dev, XL_dev, out_dev, B,
-                                cfg->n_frames, (cudaStream_t)stream, phase_cycles_dev);
+    // split path (debug hook only): the scratch area is allocated here for the duration of the call
+    void* scr = nullptr;
+    const size_t scr_bytes = mode == KASF_MODE_TEMPORAL ? module_scratch_bytes(B, cfg->n_frames) : 0;
+    if (scr_bytes && cudaMalloc(&scr, scr_bytes) != cudaSuccess) return KASF_ENOMEM;
+    rc = launch_former_module((const uint8_t*)packed_dev, layer, kind, mode, in_dev, XL_dev, out_dev, B,
+                              cfg->n_frames, (cudaStream_t)stream, phase_cycles_dev, scr, scr_bytes);
+    if (scr) {
+        cudaStreamSynchronize((cudaStream_t)stream);
+        cudaFree(scr);
+    }
+    return rc;
 }
 
 int kasf_former_module_profiled_lt(const kasf_config* cfg, const void* packed_dev, int layer, int kind, int mode,

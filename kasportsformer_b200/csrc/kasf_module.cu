@@ -1572,6 +1572,14 @@ __global__ void __launch_bounds__(256, MINB) long_attention_kernel(const ModPara
     const __nv_bfloat16* gk = p.sk + seq * T * D;
     const __nv_bfloat16* gv = p.sv + seq * T * D;
     const uint32_t rows = la_rows(T), LA_TILE = rows * 256u;   // one [rows x 128 bf16] tile
+    long long pt0 = p.prof ? clock64() : 0;                    // phase-cycle hook: thread 0's timeline, slots 8..10
+    auto mark = [&](int k) {
+        if (p.prof && tid == 0) {
+            const long long t1 = clock64();
+            atomicAdd(p.prof + k, (unsigned long long)(t1 - pt0));
+            pt0 = t1;
+        }
+    };
     // ---- load (16-byte chunks, coalesced), zero the tail rows
     for (uint32_t i = tid; i < 3 * rows * 16; i += 256) {
         const uint32_t m = i / (rows * 16), r = (i >> 4) % rows, c = i & 15;
@@ -1586,6 +1594,7 @@ __global__ void __launch_bounds__(256, MINB) long_attention_kernel(const ModPara
     cp_async_commit();
     cp_async_wait_all();
     __syncthreads();
+    mark(8);
     const uint32_t qb = smem_u32(sm), kb = smem_u32(sm + LA_TILE), vb = smem_u32(sm + 2 * LA_TILE);
     const int h = warp;
     const int g8 = lane >> 2, t4 = lane & 3, mi = lane >> 3, r8 = lane & 7;
@@ -1701,10 +1710,12 @@ __global__ void __launch_bounds__(256, MINB) long_attention_kernel(const ModPara
         }
     }
     __syncthreads();
+    mark(9);
     for (int i = tid; i < T * 16; i += 256) {
         const int r = i >> 4, c = i & 15;
         *reinterpret_cast<uint4*>(gq + (size_t)r * D + c * 8) = *reinterpret_cast<const uint4*>(sm + la_off(r, c));
     }
+    mark(10);
 }
 
 // ---- temporal GCN adjacency + aggregation of one (clip, joint) sequence, T <= 256 (graph.py:99-134)
