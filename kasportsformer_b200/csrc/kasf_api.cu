@@ -22,7 +22,9 @@ int clip_chunk(const kasf_config* cfg, int B) {
     const long long per_clip = (long long)cfg->n_frames * J * D * 4 * 6;
     long long c = (3LL << 30) / per_clip;   // ~3 GiB of streams
     if (c < 1) c = 1;
-    return (int)(c < B ? c : B);
+    if (c >= B) return B > 0 ? B : 1;
+    const long long passes = (B + c - 1) / c;            // equal passes: a 3-clip remainder pass costs a full set of launches
+    return (int)((B + passes - 1) / passes);
 }
 
 struct Streams {

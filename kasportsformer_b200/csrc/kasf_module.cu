@@ -1561,17 +1561,21 @@ __global__ void __launch_bounds__(256, 1) long_pre_kernel(const ModParams p) {
 //      The tiles hold the sequence padded to whole 64-key blocks (la_rows), so sequences of up to 128 frames take
 //      half the shared memory and two CTAs share an SM (MINB = 2).
 __host__ __device__ constexpr uint32_t la_rows(int T) { return (uint32_t)((T + 63) & ~63); }
-__device__ __forceinline__ uint32_t la_off(uint32_t r, uint32_t c16) { return r * 256u + ((c16 ^ (r & 7u)) << 4); }
+//      A CTA owns FOUR heads of a sequence (64 of the 128 columns; grid = 2 x sequences, 4 warps): the tiles are half
+//      as large, so two CTAs (four for T <= 128) share an SM and the load / store phases of one -- 17 % of the
+//      run time of the first, one-CTA-per-SM version -- run under the arithmetic of the others.
+__device__ __forceinline__ uint32_t la_off(uint32_t r, uint32_t c16) { return r * 128u + ((c16 ^ (r & 7u)) << 4); }
 
 template <int MINB>
-__global__ void __launch_bounds__(256, MINB) long_attention_kernel(const ModParams p) {
+__global__ void __launch_bounds__(128, MINB) long_attention_kernel(const ModParams p) {
     extern __shared__ __align__(1024) uint8_t sm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, T = p.T;
-    const long long seq = blockIdx.x;
-    __nv_bfloat16* gq = p.sq + seq * T * D;
-    const __nv_bfloat16* gk = p.sk + seq * T * D;
-    const __nv_bfloat16* gv = p.sv + seq * T * D;
-    const uint32_t rows = la_rows(T), LA_TILE = rows * 256u;   // one [rows x 128 bf16] tile
+    const long long seq = blockIdx.x >> 1;
+    const int hg = blockIdx.x & 1;                              // head group: columns 64 hg .. 64 hg + 63
+    __nv_bfloat16* gq = p.sq + seq * T * D + hg * 64;
+    const __nv_bfloat16* gk = p.sk + seq * T * D + hg * 64;
+    const __nv_bfloat16* gv = p.sv + seq * T * D + hg * 64;
+    const uint32_t rows = la_rows(T), LA_TILE = rows * 128u;   // one [rows x 64 bf16] tile
     long long pt0 = p.prof ? clock64() : 0;                    // phase-cycle hook: thread 0's timeline, slots 8..10
     auto mark = [&](int k) {
         if (p.prof && tid == 0) {
@@ -1581,8 +1585,8 @@ __global__ void __launch_bounds__(256, MINB) long_attention_kernel(const ModPara
         }
     };
     // ---- load (16-byte chunks, coalesced), zero the tail rows
-    for (uint32_t i = tid; i < 3 * rows * 16; i += 256) {
-        const uint32_t m = i / (rows * 16), r = (i >> 4) % rows, c = i & 15;
+    for (uint32_t i = tid; i < 3 * rows * 8; i += 128) {
+        const uint32_t m = i / (rows * 8), r = (i >> 3) % rows, c = i & 7;
         uint8_t* dst = sm + m * LA_TILE + la_off(r, c);
         if (r < T) {
             const __nv_bfloat16* src = (m == 0 ? gq : (m == 1 ? gk : gv)) + (size_t)r * D + c * 8;
@@ -1711,8 +1715,8 @@ __global__ void __launch_bounds__(256, MINB) long_attention_kernel(const ModPara
     }
     __syncthreads();
     mark(9);
-    for (int i = tid; i < T * 16; i += 256) {
-        const int r = i >> 4, c = i & 15;
+    for (int i = tid; i < T * 8; i += 128) {
+        const int r = i >> 3, c = i & 7;
         *reinterpret_cast<uint4*>(gq + (size_t)r * D + c * 8) = *reinterpret_cast<const uint4*>(sm + la_off(r, c));
     }
     mark(10);
@@ -1917,13 +1921,13 @@ static int launch_long(ModParams p, int kind, void* scratch, size_t scratch_byte
         long_pre_kernel<KASF_KIND_BONE><<<pre_grid, 256, SM_TOTAL, st>>>(p);
     }
     if ((rc = cuda_status())) return rc;
-    const int la_bytes = 3 * (int)la_rows(p.T) * 256;
+    const int la_bytes = 3 * (int)la_rows(p.T) * 128;
     if (p.T <= 128) {
-        cudaFuncSetAttribute(long_attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, la_bytes);
-        long_attention_kernel<2><<<seqs, 256, la_bytes, st>>>(p);
+        cudaFuncSetAttribute(long_attention_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, la_bytes);
+        long_attention_kernel<4><<<2 * seqs, 128, la_bytes, st>>>(p);
     } else {
-        cudaFuncSetAttribute(long_attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, la_bytes);
-        long_attention_kernel<1><<<seqs, 256, la_bytes, st>>>(p);
+        cudaFuncSetAttribute(long_attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, la_bytes);
+        long_attention_kernel<2><<<2 * seqs, 128, la_bytes, st>>>(p);
     }
     if ((rc = cuda_status())) return rc;
     return kind == KASF_KIND_ATTENTION ? launch_one<KASF_KIND_ATTENTION, KASF_MODE_LONG, 0>(p, st)
