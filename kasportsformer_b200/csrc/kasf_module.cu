@@ -1566,7 +1566,7 @@ __host__ __device__ constexpr uint32_t la_rows(int T) { return (uint32_t)((T + 6
 //      run time of the first, one-CTA-per-SM version -- run under the arithmetic of the others.
 __device__ __forceinline__ uint32_t la_off(uint32_t r, uint32_t c16) { return r * 128u + ((c16 ^ (r & 7u)) << 4); }
 
-template <int MINB>
+template <int MINB, int NKB>
 __global__ void __launch_bounds__(128, MINB) long_attention_kernel(const ModParams p) {
     extern __shared__ __align__(1024) uint8_t sm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, T = p.T;
@@ -1604,6 +1604,102 @@ __global__ void __launch_bounds__(128, MINB) long_attention_kernel(const ModPara
     const int g8 = lane >> 2, t4 = lane & 3, mi = lane >> 3, r8 = lane & 7;
     const float scale = 0.25f * 1.4426950408889634f;
     const int mtiles = (T + 15) >> 4, nkb = (T + 63) >> 6;        // 16-query blocks, 64-key blocks
+    if constexpr (NKB > 0) {
+        // ---- single pass, NKB = nkb key blocks: ALL scores of a query block stay in registers (32 NKB per thread and
+        //      block), so Q K^T is computed once -- the two-pass form below computes it twice, a third of the kernel's
+        //      mma.sync work.  Same arithmetic and rounding (global row maximum first).  With one CTA per SM this form
+        //      was slower (all warps in their mma-only and MUFU-only phases at the same time); with two to four
+        //      independent CTAs per SM the phases of different CTAs overlap.
+        constexpr int U = NKB <= 2 ? 2 : 1, NT = NKB * 8;
+#pragma unroll 1
+        for (int mt0 = 0; mt0 < mtiles; mt0 += U) {
+            uint32_t qa[U][4];
+            float s[U][NT][4];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int mt = min(mt0 + u, mtiles - 1);             // (odd count: the last round repeats a block)
+                ldsm_x4(qb + la_off(mt * 16 + (mi & 1) * 8 + r8, 2 * h + (mi >> 1)), qa[u]);
+            }
+#pragma unroll
+            for (int nt = 0; nt < NT; nt += 2) {
+                uint32_t kf[4];
+                ldsm_x4(kb + la_off(8 * (nt + (mi >> 1)) + r8, 2 * h + (mi & 1)), kf);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) s[u][nt][i] = 0.f, s[u][nt + 1][i] = 0.f;
+                    mma_bf16_16816(s[u][nt], qa[u], kf[0], kf[1]);
+                    mma_bf16_16816(s[u][nt + 1], qa[u], kf[2], kf[3]);
+                }
+            }
+            float nm0[U], nm1[U], l0[U], l1[U], o[U][2][4];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                for (int nt = NT - 8; nt < NT; ++nt)                  // only the last key block holds keys past the end
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (nt * 8 + t4 * 2 + (i & 1) >= T) s[u][nt][i] = -INFINITY;
+                float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    mx0 = fmaxf(mx0, fmaxf(s[u][nt][0], s[u][nt][1]));
+                    mx1 = fmaxf(mx1, fmaxf(s[u][nt][2], s[u][nt][3]));
+                }
+                mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+                mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+                mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+                mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+                nm0[u] = -mx0 * scale, nm1[u] = -mx1 * scale;
+                l0[u] = 0.f, l1[u] = 0.f;
+#pragma unroll
+                for (int dn = 0; dn < 2; ++dn)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) o[u][dn][i] = 0.f;
+            }
+#pragma unroll
+            for (int kblk = 0; kblk < NKB; ++kblk) {
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int nt = kblk * 8; nt < kblk * 8 + 8; ++nt) {
+                        s[u][nt][0] = ex2_approx(fmaf(s[u][nt][0], scale, nm0[u])), s[u][nt][1] = ex2_approx(fmaf(s[u][nt][1], scale, nm0[u]));
+                        s[u][nt][2] = ex2_approx(fmaf(s[u][nt][2], scale, nm1[u])), s[u][nt][3] = ex2_approx(fmaf(s[u][nt][3], scale, nm1[u]));
+                        l0[u] += s[u][nt][0] + s[u][nt][1];
+                        l1[u] += s[u][nt][2] + s[u][nt][3];
+                    }
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    uint32_t vf[4];
+                    ldsm_x4_t(vb + la_off(kblk * 64 + 16 * ks + (mi & 1) * 8 + r8, 2 * h + (mi >> 1)), vf);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int n0 = kblk * 8 + 2 * ks;
+                        uint32_t pa[4];
+                        pa[0] = pack_bf16(s[u][n0][0], s[u][n0][1]), pa[1] = pack_bf16(s[u][n0][2], s[u][n0][3]);
+                        pa[2] = pack_bf16(s[u][n0 + 1][0], s[u][n0 + 1][1]), pa[3] = pack_bf16(s[u][n0 + 1][2], s[u][n0 + 1][3]);
+                        mma_bf16_16816(o[u][0], pa, vf[0], vf[1]);
+                        mma_bf16_16816(o[u][1], pa, vf[2], vf[3]);
+                    }
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (mt0 + u < mtiles) {
+                    l0[u] += __shfl_xor_sync(0xffffffffu, l0[u], 1), l1[u] += __shfl_xor_sync(0xffffffffu, l1[u], 1);
+                    l0[u] += __shfl_xor_sync(0xffffffffu, l0[u], 2), l1[u] += __shfl_xor_sync(0xffffffffu, l1[u], 2);
+                    const float i0 = rcp_approx(l0[u]), i1 = rcp_approx(l1[u]);
+#pragma unroll
+                    for (int dn = 0; dn < 2; ++dn) {
+                        const int r0 = (mt0 + u) * 16 + g8, r1 = r0 + 8;
+                        *reinterpret_cast<uint32_t*>(sm + la_off(r0, 2 * h + dn) + t4 * 4) = pack_bf16(o[u][dn][0] * i0, o[u][dn][1] * i0);
+                        *reinterpret_cast<uint32_t*>(sm + la_off(r1, 2 * h + dn) + t4 * 4) = pack_bf16(o[u][dn][2] * i1, o[u][dn][3] * i1);
+                    }
+                }
+            }
+        }
+    } else {
     // Two query blocks per round (U = 2): their ldmatrix -> mma -> ex2 -> mma chains are independent, which is the
     // only instruction-level parallelism a warp has here (one block at a time left both pipes mostly idle; keeping
     // all scores of a block in registers for a single pass was slower still: the eight warps then run their
@@ -1712,6 +1808,7 @@ __global__ void __launch_bounds__(128, MINB) long_attention_kernel(const ModPara
                 }
             }
         }
+    }
     }
     __syncthreads();
     mark(9);
@@ -1922,13 +2019,17 @@ static int launch_long(ModParams p, int kind, void* scratch, size_t scratch_byte
     }
     if ((rc = cuda_status())) return rc;
     const int la_bytes = 3 * (int)la_rows(p.T) * 128;
-    if (p.T <= 128) {
-        cudaFuncSetAttribute(long_attention_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, la_bytes);
-        long_attention_kernel<4><<<2 * seqs, 128, la_bytes, st>>>(p);
-    } else {
-        cudaFuncSetAttribute(long_attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, la_bytes);
-        long_attention_kernel<2><<<2 * seqs, 128, la_bytes, st>>>(p);
-    }
+#define KASF_LA(MINB, NKB)                                                                                     \
+    do {                                                                                                       \
+        cudaFuncSetAttribute(long_attention_kernel<MINB, NKB>, cudaFuncAttributeMaxDynamicSharedMemorySize, la_bytes); \
+        long_attention_kernel<MINB, NKB><<<2 * seqs, 128, la_bytes, st>>>(p);                                 \
+    } while (0)
+    const int nkb = (p.T + 63) >> 6;
+    if (nkb == 4) KASF_LA(2, 4);
+    else if (nkb == 3) KASF_LA(2, 3);
+    else if (nkb == 2) KASF_LA(3, 2);
+    else KASF_LA(4, 0);
+#undef KASF_LA
     if ((rc = cuda_status())) return rc;
     return kind == KASF_KIND_ATTENTION ? launch_one<KASF_KIND_ATTENTION, KASF_MODE_LONG, 0>(p, st)
                                        : launch_one<KASF_KIND_BONE, KASF_MODE_LONG, 0>(p, st);
