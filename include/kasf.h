@@ -125,7 +125,7 @@ int    kasf_forward_ex(const kasf_config* cfg, const void* packed_dev, const flo
 /* Number of kernel launches one kasf_forward(B) enqueues (for bench accounting). */
 int    kasf_forward_launches(const kasf_config* cfg, int B);
 /* Number of timing marks of kasf_forward_timed: one per stage (features, every FormerModule, every fusion,
- * head).  Equal to the launch count for n_frames <= 128; for longer sequences a temporal module is 2-3
+ * head).  Equal to the launch count for n_frames <= 64; for longer sequences a temporal module is 2-3
  * kernels behind one mark. */
 int    kasf_forward_marks(const kasf_config* cfg, int B);
 /* Same forward, additionally recording events[0] before the first stage and events[i] after the
@@ -155,10 +155,10 @@ int kasf_kinematic_features(const kasf_config* cfg, const void* packed_dev, cons
 int kasf_former_module(const kasf_config* cfg, const void* packed_dev, int layer, int kind,
                        int mode, const float* in_dev, const float* XL_dev, float* out_dev, int B,
                        void* stream);
-/* Same with caller-provided scratch.  Temporal modules of sequences longer than one 128-row tile
- * (n_frames > 128, e.g. the T=243 configs) run as a projection kernel, a per-sequence mixer-core kernel
+/* Same with caller-provided scratch.  Temporal modules of sequences that do not pack into a 128-row tile
+ * (n_frames > 64: the T=81 and T=243 configs) run as a projection kernel, a per-sequence mixer-core kernel
  * and the fused tail, exchanging bf16 Q/K/V (or A_hat z) through `scratch_dev`
- * (>= kasf_module_scratch_bytes(cfg, B) bytes, 256-byte aligned; 0 bytes needed for n_frames <= 128,
+ * (>= kasf_module_scratch_bytes(cfg, B) bytes, 256-byte aligned; 0 bytes needed for n_frames <= 64,
  * then identical to kasf_former_module).  kasf_former_module returns KASF_ENOMEM in that case. */
 size_t kasf_module_scratch_bytes(const kasf_config* cfg, int B);
 int kasf_former_module_ws(const kasf_config* cfg, const void* packed_dev, int layer, int kind,
@@ -170,8 +170,8 @@ int kasf_former_module_ws(const kasf_config* cfg, const void* packed_dev, int la
  * normalises XL once (fp32 two-pass statistics, model/modules/bone_crossattention.py:47-51) and writes it as bf16
  * [128 x 128] operand tiles in the tile order of `mode`; a bone module of the same mode given `limb_tiles_dev`
  * (128-byte aligned, kasf_limb_tiles_bytes bytes) fetches its K|V operand with one bulk copy per tile and never
- * reads XL_dev.  kasf_limb_tiles_bytes is 0 for temporal tiles with n_frames > 128 (the split path reads XL_dev);
- * pass NULL then.  kasf_forward uses this path internally. */
+ * reads XL_dev (temporal tiles of n_frames > 64 are in the split path's (sequence, frame) row order).  Without
+ * limb tiles (NULL) the module normalises the fp32 limb rows itself.  kasf_forward uses this path internally. */
 size_t kasf_limb_tiles_bytes(const kasf_config* cfg, int B, int mode);
 int kasf_limb_tiles(const kasf_config* cfg, const float* XL_dev, void* limb_tiles_dev, int B, int mode,
                     void* stream);

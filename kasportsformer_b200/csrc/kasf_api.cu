@@ -161,10 +161,9 @@ int kasf_forward_launches(const kasf_config* cfg, int B) {
     if (config_ok(cfg) || B <= 0) return 0;
     const int chunk = clip_chunk(cfg, B);
     const int passes = (B + chunk - 1) / chunk;
-    // T > 128: a temporal module is 3 kernels (attention, bone) or 2 (graph) instead of 1
+    // T > KASF_SPLIT_T: a temporal module is 3 kernels (attention, bone) or 2 (graph) instead of 1
     const int per_layer = cfg->n_frames > KASF_SPLIT_T ? 7 + 2 + 1 + 2 : 7;
-    const int limb = cfg->n_frames > KASF_SPLIT_T ? 1 : 2;   // limb_tiles_kernel launches
-    return passes * (1 + limb + cfg->n_layers * per_layer + 1);
+    return passes * (1 + 2 /* limb_tiles_kernel, spatial + temporal */ + cfg->n_layers * per_layer + 1);
 }
 
 int kasf_kinematic_features(const kasf_config* cfg, const void* packed_dev, const float* x_dev, float* bone_dev,
@@ -317,10 +316,10 @@ static int forward_impl(const kasf_config* cfg, const void* packed_dev, const fl
         const long long tokens = (long long)nb * T * J;
         Streams s = carve(ws_dev, (long long)chunk * T * J);
         const size_t stream_bytes = ((size_t)chunk * T * J * D * 4 + 1023) / 1024 * 1024;
-        void* scr = static_cast<uint8_t*>(ws_dev) + 6 * stream_bytes;     // temporal modules, T > 128 only
+        void* scr = static_cast<uint8_t*>(ws_dev) + 6 * stream_bytes;     // temporal modules, T > KASF_SPLIT_T only
         const size_t scr_bytes = module_scratch_bytes(chunk, T);
         // normalised limb rows as bf16 operand tiles (spatial / temporal tile order), shared by all layers
-        // (T > 128: one scratch area per branch, the branches run concurrently)
+        // (split path: one scratch area per branch, the branches run concurrently)
         void* scr_g = static_cast<uint8_t*>(scr) + scr_bytes;
         void* scr_b = static_cast<uint8_t*>(scr) + 2 * scr_bytes;
         uint8_t* lt_s = static_cast<uint8_t*>(scr) + 3 * scr_bytes;

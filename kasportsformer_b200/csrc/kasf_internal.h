@@ -39,12 +39,12 @@ int launch_head(const uint8_t* blob, const float* X, float* y, float* rep, long 
                 bool tensor_cores = true);
 int launch_fusion(const uint8_t* blob, int layer, const float* a, const float* g, const float* b, float* out,
                   long long tokens, cudaStream_t st);
-// `scratch` (module_scratch_bytes(B, T) bytes, 256-byte aligned) is needed by temporal modules with T > 128 only
+// `scratch` (module_scratch_bytes(B, T) bytes, 256-byte aligned) is needed by temporal modules with T > KASF_SPLIT_T only
 int launch_former_module(const uint8_t* blob, int layer, int kind, int mode, const float* in, const float* XL,
                          float* out, int B, int T, cudaStream_t st, unsigned long long* prof = nullptr,
                          void* scratch = nullptr, size_t scratch_bytes = 0, const void* limb_tiles = nullptr,
                          unsigned flags = 0);
-// Pre-normalised limb rows as bf16 operand tiles in the tile order of `mode` (0 bytes for temporal, T > 128): the
+// Pre-normalised limb rows as bf16 operand tiles in the tile order of `mode` (temporal, T > KASF_SPLIT_T: split-path row order): the
 // optional `limb_tiles` argument of a bone module of the same mode.
 size_t limb_tiles_bytes(int B, int T, int mode);
 int launch_limb_tiles(const float* XL, void* tiles, int B, int T, int mode, cudaStream_t st);

@@ -31,7 +31,7 @@ struct Lay {
     static constexpr uint32_t ZH = 0, ZM = PIECE, ZL = 2 * PIECE;
     static constexpr uint32_t RSD = 3 * PIECE;            // f32 [ROWS]
     static constexpr uint32_t ADJ = RSD + ROWS * 4;       // u32 [ROWS / 32][ROWS]: adjacency bits, word-major (conflict-free)
-    static constexpr uint32_t BARS = ADJ + ROWS * ROWS / 8;   // S ready [2], aggregation ready [2], tmem slot
+    static constexpr uint32_t BARS = ADJ + ROWS * ROWS / 8;   // S ready [2], aggregation ready [2], images ready, rescaled ready; tmem slot
     static constexpr uint32_t TOTAL = BARS + 64;
     static constexpr uint32_t TM_COLS = 256 * MT;         // per M-tile 256 columns: S [0, ROWS) -> P [0, ROWS/2); O [128, 256)
 };
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(128 * MT + 32, MT == 1 ? 2 : 1) long_gcn_tc_ke
     constexpr int ROWS = L::ROWS, NW = 4 * MT, RPW = ROWS / NW, NCH = ROWS / 32;
     extern __shared__ __align__(1024) uint8_t sm[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::BARS);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L::BARS + 32);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L::BARS + 56);
     float* rsd = reinterpret_cast<float*>(sm + L::RSD);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, T = p.T;
     const long long seq = blockIdx.x, b = seq / J;
@@ -75,14 +75,24 @@ __global__ void __launch_bounds__(128 * MT + 32, MT == 1 ? 2 : 1) long_gcn_tc_ke
             pt0 = t1;
         }
     };
+    // The issuer warp is driven by mbarriers only (images ready / rescaled images ready, one arrival per row warp);
+    // the row warps meet each other at a named barrier of their own.
+    auto row_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(128 * MT) : "memory"); };
+    enum { B_S = 0, B_AGG = 2, B_IMG = 4, B_RESC = 5 };
     if (tid == 0) {
         for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+        mbar_init(&bars[B_IMG], NW);
+        mbar_init(&bars[B_RESC], NW);
         fence_mbar_init();
     }
     if (warp == 0) {
         tmem_alloc(tmem_slot, L::TM_COLS);
         tmem_relinquish();
     }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
     mark(11);
     const uint32_t zb = smem_u32(sm);
     // =============================================================================== MMA issuer (one extra warp)
@@ -90,34 +100,29 @@ __global__ void __launch_bounds__(128 * MT + 32, MT == 1 ? 2 : 1) long_gcn_tc_ke
     // similarity MMAs; with the issue in a warp of its own the row warps of M-tile 0 take their thresholds while the
     // MMAs of M-tile 1 run.
     if (warp == NW) {
-        tc_fence_before();
-        __syncthreads();                                   // A: operand images complete
-        tc_fence_after();
-        const uint32_t tmem = *tmem_slot;
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(128, ROWS);
-            const uint32_t pa[6] = {L::ZM, L::ZH, L::ZL, L::ZH, L::ZM, L::ZH};      // six piece products, smallest first
-            const uint32_t pb[6] = {L::ZM, L::ZL, L::ZH, L::ZM, L::ZH, L::ZH};
+            mbar_wait(&bars[B_IMG], 0);                    // operand images complete
+            tc_fence_after();
+            {
+                const uint32_t idesc = umma_idesc_bf16(128, ROWS);
+                const uint32_t pa[6] = {L::ZM, L::ZH, L::ZL, L::ZH, L::ZM, L::ZH};      // six piece products, smallest first
+                const uint32_t pb[6] = {L::ZM, L::ZL, L::ZH, L::ZM, L::ZH, L::ZH};
 #pragma unroll 1
-            for (int mt = 0; mt < MT; ++mt) {
+                for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll 1
-                for (int pr = 0; pr < 6; ++pr) {
+                    for (int pr = 0; pr < 6; ++pr) {
 #pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) {
-                        const uint32_t koff = (ks >> 2) * L::CB + (ks & 3) * 32u;
-                        umma_bf16(tmem + mt * 256, umma_desc_sw128(zb + pa[pr] + koff + mt * 16384u),
-                                  umma_desc_sw128(zb + pb[pr] + koff), idesc, (pr | ks) ? 1u : 0u);
+                        for (int ks = 0; ks < 8; ++ks) {
+                            const uint32_t koff = (ks >> 2) * L::CB + (ks & 3) * 32u;
+                            umma_bf16(tmem + mt * 256, umma_desc_sw128(zb + pa[pr] + koff + mt * 16384u),
+                                      umma_desc_sw128(zb + pb[pr] + koff), idesc, (pr | ks) ? 1u : 0u);
+                        }
                     }
+                    tc_commit(&bars[B_S + mt]);
                 }
-                tc_commit(&bars[mt]);
             }
-        }
-        __syncwarp();
-        tc_fence_before();
-        __syncthreads();                                   // B: adjacency rows in tensor memory, similarity consumed
-        __syncthreads();                                   // C: rescaled images complete
-        tc_fence_after();
-        if (lane == 0) {
+            mbar_wait(&bars[B_RESC], 0);                   // adjacency rows in tensor memory, rescaled images complete
+            tc_fence_after();
             const uint32_t idesc = umma_idesc_bf16(128, 128) | (1u << 16);       // B operand MN-major
 #pragma unroll 1
             for (int m2 = 0; m2 < MT; ++m2) {
@@ -129,12 +134,9 @@ __global__ void __launch_bounds__(128 * MT + 32, MT == 1 ? 2 : 1) long_gcn_tc_ke
                         umma_ts(tmem + m2 * 256 + 128, tmem + m2 * 256 + ks * 8, desc_mn_sw128(img + ks * 2048u, L::CB), idesc,
                                 (pc | ks) ? 1u : 0u);
                 }
-                tc_commit(&bars[2 + m2]);
+                tc_commit(&bars[B_AGG + m2]);
             }
         }
-        __syncwarp();
-        tc_fence_before();
-        __syncthreads();                                   // D
         return;
     }
     // ================================================================================================ row warps
@@ -206,18 +208,15 @@ __global__ void __launch_bounds__(128 * MT + 32, MT == 1 ? 2 : 1) long_gcn_tc_ke
             for (int u = 0; u < RB; ++u) xa[u] = xb[u], xb[u] = xc[u];
         }
     }
-    mark(13);
     fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();                                       // A
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bars[B_IMG]);
     mark(0);
     // ---- 3. thread = row: threshold, adjacency bits, degree (tcgen05.ld of chunk c + 1 in flight under chunk c)
     const int mt = warp >> 2, row = mt * 128 + (warp & 3) * 32 + lane;
     const uint32_t tb = tmem + ((uint32_t)((warp & 3) * 32) << 16) + mt * 256;
     const int nch = (T + 31) >> 5;                         // chunks of 32 frames that hold valid columns
-    mbar_wait(&bars[mt], 0);
+    mbar_wait(&bars[B_S + mt], 0);
     tc_fence_after();
     mark(1);
     // (rolled loops, two chunks per trip with the second tcgen05.ld in flight under the first chunk's network; the
@@ -316,9 +315,10 @@ __global__ void __launch_bounds__(128 * MT + 32, MT == 1 ? 2 : 1) long_gcn_tc_ke
         tmem_st32(tb + c4 * 32, pw);
     }
     tmem_st_wait();
-    if (MT == 2) mbar_wait(&bars[MT - 1], 0);     // every similarity MMA has read the images before they are rescaled
+    if (MT == 2) mbar_wait(&bars[B_S + MT - 1], 0);     // every similarity MMA has read the images before they are rescaled
     tc_fence_before();
-    __syncthreads();                                       // B
+    row_sync();                                        // every row's degree is known, every similarity row consumed
+    tc_fence_after();
     mark(3);
     // ---- 4. y = d_j z_j -> two bf16 pieces over h | m (warp per row, lane = 4 columns, four rows per round);
     //         row sums of A_hat
@@ -365,10 +365,12 @@ __global__ void __launch_bounds__(128 * MT + 32, MT == 1 ? 2 : 1) long_gcn_tc_ke
         }
     }
     fence_proxy_async();
-    __syncthreads();                                       // C
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bars[B_RESC]);
     mark(4);
     // ---- 5. d_i (A y) -> bf16 scratch rows; row sums
-    mbar_wait(&bars[2 + mt], 0);
+    mbar_wait(&bars[B_AGG + mt], 0);
     tc_fence_after();
     mark(5);
     const long long R = seq * T + row;
@@ -397,7 +399,7 @@ __global__ void __launch_bounds__(128 * MT + 32, MT == 1 ? 2 : 1) long_gcn_tc_ke
     if (row < T) p.srow[R] = rs;
     mark(6);
     tc_fence_before();
-    __syncthreads();                                       // D
+    row_sync();
     if (warp == 0) tmem_dealloc(tmem, L::TM_COLS);
 }
 

@@ -106,7 +106,7 @@ struct ModParams {
     int ntiles;
     int groups_per_tile;     // temporal: sequences per tile
     unsigned long long* prof;   // optional [24] per-phase cycle counters (debug/profiling hook), else null
-    // long sequences (T > 128, split path): scratch in (sequence, frame) row order, row = seq * T + t
+    // long sequences (T > KASF_SPLIT_T, split path): scratch in (sequence, frame) row order, row = seq * T + t
     __nv_bfloat16* sq;       // [B*17*T, 128] Q, then the attention output O (in place) | GCN: A_hat z
     __nv_bfloat16* sk;       // [B*17*T, 128] K
     __nv_bfloat16* sv;       // [B*17*T, 128] V
@@ -770,7 +770,7 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
 // The compute warps never issue an MMA and (apart from the mixer cores, which exchange rows through shared
 // memory) never meet at a CTA barrier: every hand-over is an mbarrier, so warps drift apart and the MUFU-bound
 // GELU epilogues of one warp overlap the tensor-memory loads, stores and MMAs triggered by the others.
-// MODE == KASF_MODE_LONG is the tail of the split path for sequences longer than a tile (T > 128): the mixer
+// MODE == KASF_MODE_LONG is the tail of the split path for sequences that do not pack into a tile (T > KASF_SPLIT_T): the mixer
 // core ran in its own kernels (kasf_long section below) and left the attention output / A_hat z in scratch;
 // this kernel then does projection -> residual -> LN2 -> MLP -> residual on plain 128-row tiles.
 // PROF: the per-phase cycle counters of kasf_former_module_profiled are compiled in (own instantiations, so that the
@@ -1367,14 +1367,16 @@ static int launch_one(const ModParams& p, cudaStream_t st) {
 
 #include "kasf_module_v2.cuh"
 
-// ============================================================================================== split path (T > 128)
-// A temporal sequence longer than one 128-row tile (T = 243) does not fit the fused kernel's "a tile owns whole
-// groups" scheme, so the module runs as three kernels over scratch in (sequence, frame) row order:
-//   attention / bone:  long_pre_kernel (LN1 [, LN_limb] -> Q, K, V on tcgen05 -> bf16 scratch)
-//                      long_attention_kernel (one CTA per sequence: softmax(q k^T / 4) v, Q|K|V resident in smem)
+// ============================================================================================== split path (T > KASF_SPLIT_T)
+// A temporal sequence that does not pack into a 128-row tile -- longer than the tile (T = 243), or so long that one
+// sequence per tile would leave a third of the MMA rows empty (T = 81) -- runs as two or three kernels over bf16
+// scratch in (sequence, frame) row order:
+//   attention / bone:  long_pre_kernel (LN1 [, limb operand] -> Q, K, V on tcgen05 -> bf16 scratch)
+//                      long_attention_kernel (one CTA per sequence and four heads: softmax(q k^T / 4) v)
 //                      former_module_kernel<KIND, KASF_MODE_LONG> (projection, residual, LN2, MLP, residual)
-//   graph:             long_gcn_kernel (one CTA per sequence: z = LN1(x) fp32 in smem, 3xTF32 similarity, exact
-//                      4th-largest threshold, degrees, A_hat z and row sums -> scratch)
+//   graph:             lgt::long_gcn_tc_kernel (kasf_long_gcn.cuh, one CTA per sequence: z = LN1(x) as three bf16
+//                      pieces, fp32-accurate similarity, exact 4th-largest threshold, degrees, A_hat z and row sums
+//                      on the tcgen05 tensor cores -> scratch)
 //                      former_module_kernel<GRAPH, KASF_MODE_LONG> (U z + (A_hat z) V^T, BN, residuals, MLP)
 // Same arithmetic as the fused kernels (bf16 operands, fp32 accumulation / statistics / softmax / similarity).
 
@@ -1472,9 +1474,8 @@ __global__ void __launch_bounds__(256, 1) long_pre_kernel(const ModParams p) {
                     mbar_wait(&bars[BL], ph_l);
                     tc_fence_after();
                     umma_tile_k128(tmem + TM_K, a_addr, ring, 128, false);
-                    tc_commit(&bars[BK]);
                     umma_tile_k128(tmem + TM_V, a_addr, ring + CHUNK_BYTES, 128, false);
-                    tc_commit(&bars[BV]);
+                    tc_commit(&bars[BV]);                  // (one barrier for both: nobody waits for K alone)
                 }
                 ph_l ^= 1;
             } else {
@@ -1489,9 +1490,8 @@ __global__ void __launch_bounds__(256, 1) long_pre_kernel(const ModParams p) {
                 if (tid == 0) {
                     tc_fence_after();
                     umma_tile_k128(tmem + TM_K, a_addr, ring, 128, false);
-                    tc_commit(&bars[BK]);
                     umma_tile_k128(tmem + TM_V, a_addr, ring + CHUNK_BYTES, 128, false);
-                    tc_commit(&bars[BV]);
+                    tc_commit(&bars[BV]);                  // (one barrier for both: nobody waits for K alone)
                 }
                 gather_rows<KASF_MODE_LONG>(p, sm, tile, p.in, &bars[BR], warp, lane, 0);
                 gather_rows<KASF_MODE_LONG>(p, sm, tile, p.in, &bars[BR], warp, lane, 1);
@@ -1502,7 +1502,7 @@ __global__ void __launch_bounds__(256, 1) long_pre_kernel(const ModParams p) {
         read_staged(sm, e, xv, row_ok);
         ln_stats(sm, e, xv, mean, rstd);
         if (KIND == KASF_KIND_BONE) {
-            mbar_wait(&bars[BV], ph_m);                    // K, V MMAs (committed in this order) have read the limb operand
+            mbar_wait(&bars[BV], ph_m);                    // K, V MMAs have read the limb operand
             tc_fence_after();
         }
         ln_write<false, false>(sm, SM_A0, e, xv, mean, rstd, nullptr, nullptr, row_ok);
@@ -1817,172 +1817,6 @@ __global__ void __launch_bounds__(128, MINB) long_attention_kernel(const ModPara
         *reinterpret_cast<uint4*>(gq + (size_t)r * D + c * 8) = *reinterpret_cast<const uint4*>(sm + la_off(r, c));
     }
     mark(10);
-}
-
-// ---- temporal GCN adjacency + aggregation of one (clip, joint) sequence, T <= 256 (graph.py:99-134)
-constexpr uint32_t LG_Z = 0;                       // fp32 [256][128], f32_off layout
-constexpr uint32_t LG_ADJ = 256 * 512;             // u32 [256][8]
-constexpr uint32_t LG_RSD = LG_ADJ + 256 * 32;     // f32 [256]
-constexpr uint32_t LG_TOTAL = LG_RSD + 1024;
-
-__global__ void __launch_bounds__(256, 1) long_gcn_kernel(const ModParams p) {
-    extern __shared__ __align__(1024) uint8_t sm[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, T = p.T;
-    const long long seq = blockIdx.x, b = seq / J;
-    const int j = (int)(seq % J);
-    const float* vecg = reinterpret_cast<const float*>(p.mod);
-    uint32_t* adj = reinterpret_cast<uint32_t*>(sm + LG_ADJ);
-    float* rsd = reinterpret_cast<float*>(sm + LG_RSD);
-    // ---- z = LN1(x) in fp32, warp per row (lane = 4 columns), exact two-pass statistics
-    const float4 gam = *reinterpret_cast<const float4*>(vecg + V_N1W + lane * 4);
-    const float4 bet = *reinterpret_cast<const float4*>(vecg + V_N1B + lane * 4);
-    for (int r = warp; r < 256; r += 8) {
-        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < T) {
-            const float4 x = *reinterpret_cast<const float4*>(p.in + (((b * T + r) * J + j) * D) + lane * 4);
-            float s = (x.x + x.y) + (x.z + x.w);
-#pragma unroll
-            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            const float mean = s * (1.0f / D);
-            const float d0 = x.x - mean, d1 = x.y - mean, d2 = x.z - mean, d3 = x.w - mean;
-            float q = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3)));
-#pragma unroll
-            for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-            const float rstd = 1.0f / sqrtf(q * (1.0f / D) + 1e-5f);
-            z.x = fmaf(d0 * rstd, gam.x, bet.x), z.y = fmaf(d1 * rstd, gam.y, bet.y);
-            z.z = fmaf(d2 * rstd, gam.z, bet.z), z.w = fmaf(d3 * rstd, gam.w, bet.w);
-        }
-        *reinterpret_cast<float4*>(sm + LG_Z + f32_off(r, lane)) = z;
-    }
-    __syncthreads();
-    // ---- similarity rows (3xTF32) and the 4th-largest threshold, 16 rows per work item
-    const int g8 = lane >> 2, t4 = lane & 3;
-    const int mtiles = (T + 15) >> 4, nkt = (T + 7) >> 3;
-#pragma unroll 1
-    for (int mt = warp; mt < mtiles; mt += 8) {
-        const int ra = mt * 16 + g8, rb = ra + 8;               // < 256: rows >= T are zero
-        float s[32][4];
-#pragma unroll
-        for (int nt = 0; nt < 32; ++nt)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) s[nt][i] = 0.f;
-        // K = 128 in eight double steps of 16 columns, 128-bit operand loads with the k permutation of
-        // similarity_topk_impl (lane t4 takes columns 16 d + 4 t4 .. + 3); the key rows 8 nt + g8 share the swizzle
-        // phase g8, so every B address is one base plus an immediate
-        const uint32_t zrow_a = LG_Z + ra * 512 + ((t4 ^ (ra & 7)) << 4);
-        const uint32_t zrow_b = LG_Z + rb * 512 + ((t4 ^ (rb & 7)) << 4);
-        const uint32_t zrow_j = LG_Z + g8 * 512 + ((t4 ^ g8) << 4);
-        auto split = [](float v, uint32_t& hi, uint32_t& lo) {
-            hi = __float_as_uint(v) & 0xffffe000u;
-            lo = __float_as_uint(v - __uint_as_float(hi));
-        };
-#pragma unroll 1
-        for (int d = 0; d < 8; ++d) {
-            const uint32_t off = (d >> 1) * 128, flip = (d & 1) << 6;
-            const float4 fa = *reinterpret_cast<const float4*>(sm + ((zrow_a + off) ^ flip));
-            const float4 fb = *reinterpret_cast<const float4*>(sm + ((zrow_b + off) ^ flip));
-            uint32_t ah[2][4], al[2][4];
-            split(fa.x, ah[0][0], al[0][0]), split(fb.x, ah[0][1], al[0][1]), split(fa.y, ah[0][2], al[0][2]), split(fb.y, ah[0][3], al[0][3]);
-            split(fa.z, ah[1][0], al[1][0]), split(fb.z, ah[1][1], al[1][1]), split(fa.w, ah[1][2], al[1][2]), split(fb.w, ah[1][3], al[1][3]);
-            const uint8_t* bj = sm + ((zrow_j + off) ^ flip);
-#pragma unroll
-            for (int nt = 0; nt < 32; ++nt) {
-                if (nt < nkt) {
-                    const float4 fj = *reinterpret_cast<const float4*>(bj + nt * 4096);
-                    uint32_t bh[4], bl[4];
-                    split(fj.x, bh[0], bl[0]), split(fj.y, bh[1], bl[1]), split(fj.z, bh[2], bl[2]), split(fj.w, bh[3], bl[3]);
-#pragma unroll
-                    for (int k2 = 0; k2 < 2; ++k2) {
-                        mma_tf32_1688(s[nt], al[k2], bh[2 * k2], bh[2 * k2 + 1]);
-                        mma_tf32_1688(s[nt], ah[k2], bl[2 * k2], bl[2 * k2 + 1]);
-                        mma_tf32_1688(s[nt], ah[k2], bh[2 * k2], bh[2 * k2 + 1]);
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int hrow = 0; hrow < 2; ++hrow) {
-            // 4th largest with multiplicity (torch.topk) by sorting networks, as in similarity_topk_impl
-            float best[4];
-#pragma unroll
-            for (int g4 = 0; g4 < 16; ++g4) {
-                float c[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int nt = 2 * g4 + (q >> 1), i = q & 1;
-                    c[q] = (nt * 8 + t4 * 2 + i < T) ? s[nt][hrow * 2 + i] : -INFINITY;
-                }
-                sort4_desc(c);
-                if (g4 == 0) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) best[i] = c[i];
-                } else {
-                    merge_top4(best, c);
-                }
-            }
-            float o[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) o[i] = __shfl_xor_sync(0xffffffffu, best[i], 1);
-            merge_top4(best, o);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) o[i] = __shfl_xor_sync(0xffffffffu, best[i], 2);
-            const float thr = fminf(fminf(fmaxf(best[0], o[3]), fmaxf(best[1], o[2])), fminf(fmaxf(best[2], o[1]), fmaxf(best[3], o[0])));
-            const int row = mt * 16 + g8 + hrow * 8;
-            int deg = 0;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                uint32_t bits = 0;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int nt = w * 4 + q;
-#pragma unroll
-                    for (int i = 0; i < 2; ++i)
-                        if (nt * 8 + t4 * 2 + i < T && s[nt][hrow * 2 + i] >= thr) bits |= 1u << (q * 8 + t4 * 2 + i);
-                }
-                bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
-                bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
-                deg += __popc(bits);
-                if (t4 == 0 && row < T) adj[row * 8 + w] = bits;
-            }
-            if (t4 == 0 && row < T) rsd[row] = 1.0f / sqrtf((float)deg);
-        }
-    }
-    __syncthreads();
-    // ---- A_hat z (sparse gather, fp32) -> bf16 scratch; row sums of A_hat
-    for (int task = tid; task < 2 * T; task += 256) {
-        const int row = task >> 1, half = task & 1;
-        float a[64], rs = 0.f;
-#pragma unroll
-        for (int i = 0; i < 64; ++i) a[i] = 0.f;
-        const float di = rsd[row];
-#pragma unroll 1
-        for (int w = 0; w < 8; ++w) {
-            unsigned bits = adj[row * 8 + w];
-#pragma unroll 1
-            while (bits) {
-                const int jr = 32 * w + __ffs(bits) - 1;
-                bits &= bits - 1;
-                const float cf = di * rsd[jr];
-                rs += cf;
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    const float4 z = *reinterpret_cast<const float4*>(sm + LG_Z + f32_off(jr, half * 16 + c));
-                    a[c * 4] = fmaf(cf, z.x, a[c * 4]), a[c * 4 + 1] = fmaf(cf, z.y, a[c * 4 + 1]);
-                    a[c * 4 + 2] = fmaf(cf, z.z, a[c * 4 + 2]), a[c * 4 + 3] = fmaf(cf, z.w, a[c * 4 + 3]);
-                }
-            }
-        }
-        const long long R = seq * T + row;
-        __nv_bfloat16* dst = p.sq + R * D + half * 64;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            uint4 pk;
-            pk.x = pack_bf16(a[c * 8 + 0], a[c * 8 + 1]), pk.y = pack_bf16(a[c * 8 + 2], a[c * 8 + 3]);
-            pk.z = pack_bf16(a[c * 8 + 4], a[c * 8 + 5]), pk.w = pack_bf16(a[c * 8 + 6], a[c * 8 + 7]);
-            *reinterpret_cast<uint4*>(dst + c * 8) = pk;
-        }
-        if (half == 0) p.srow[R] = rs;
-    }
 }
 
 #include "kasf_long_gcn.cuh"

@@ -11,7 +11,7 @@ blob = _capi.pack_state(cfg, {k: v for k, v in state.items() if v.is_floating_po
 v = torch.randn(B, T, 17, 128, device=dev)
 xl = torch.randn(B, T, 17, 128, device=dev)
 names = {0: "ln_split", 1: "similarity_wait", 2: "threshold_bits", 3: "adjacency_store_sync", 4: "rescale_rowsum", 5: "aggregation_wait",
-         6: "epilogue", 8: "load", 9: "attention", 10: "store", 11: "dbg_alloc", 12: "dbg_first_row", 13: "dbg_ln_loop"}
+         6: "epilogue", 8: "load", 9: "attention", 10: "store", 11: "setup"}
 for kind in ("graph", "attention"):
     out = torch.empty_like(v)
     prof = torch.zeros(24, dtype=torch.int64, device=dev)

@@ -88,7 +88,7 @@ MODULES = [("att", "attention"), ("graph", "graph"), ("bone", "bone")]
 @pytest.mark.parametrize("mode", ["spatial", "temporal"])
 @pytest.mark.parametrize("br,kind", MODULES)
 def test_former_module(br, kind, mode, T, B):
-    """One FormerModule (the fused kernel; for temporal modules with T > 128 the split path: projection kernel,
+    """One FormerModule (the fused kernel; for temporal modules with T > 64 the split path: projection kernel,
     per-sequence mixer-core kernel, fused tail) vs the oracle.
 
     (a) against the oracle emulating the kernel's bf16 operand rounding: update error <= 2e-3 of the
