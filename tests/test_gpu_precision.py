@@ -38,8 +38,10 @@ def _model(meta):
 
 
 # measured on B200 (round 2, profiles/r02_precision_report.jsonl): fast-mode max |dy| against the reference golden is
-# 0.75 / 1.33 / 0.42 mm (mean 0.13 / 0.08 / 0.09 mm), exact-mode 0.0005 / 0.0004 / 0.0004 mm; the bound is ~2x the measurement
-FAST_BOUND_MM = {"stress_L2_T27.npz": 1.6, "stress_L1_T81.npz": 2.8, "stress_L1_T9.npz": 1.0}
+# 0.75 / 2.71 / 0.42 mm (mean 0.13 / 0.08 / 0.09 mm), exact-mode 0.0005 / 0.0004 / 0.0004 mm; the bound is ~2x the measurement.
+# (T = 81 runs on the split path: its maximum sits on one token behind a top-k edge that the bf16 operands of the preceding
+#  blocks moved -- 1.33 mm with the fused kernel's similarity, 2.71 mm with the split path's; the mean is unchanged.)
+FAST_BOUND_MM = {"stress_L2_T27.npz": 1.6, "stress_L1_T81.npz": 5.0, "stress_L1_T9.npz": 1.0}
 
 
 @pytest.mark.parametrize("name", ["stress_L2_T27.npz", "stress_L1_T81.npz", "stress_L1_T9.npz"])
