@@ -1566,7 +1566,7 @@ __host__ __device__ constexpr uint32_t la_rows(int T) { return (uint32_t)((T + 6
 //      run time of the first, one-CTA-per-SM version -- run under the arithmetic of the others.
 __device__ __forceinline__ uint32_t la_off(uint32_t r, uint32_t c16) { return r * 128u + ((c16 ^ (r & 7u)) << 4); }
 
-template <int MINB, int NKB>
+template <int MINB, int NT16>
 __global__ void __launch_bounds__(128, MINB) long_attention_kernel(const ModParams p) {
     extern __shared__ __align__(1024) uint8_t sm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, T = p.T;
@@ -1604,13 +1604,14 @@ __global__ void __launch_bounds__(128, MINB) long_attention_kernel(const ModPara
     const int g8 = lane >> 2, t4 = lane & 3, mi = lane >> 3, r8 = lane & 7;
     const float scale = 0.25f * 1.4426950408889634f;
     const int mtiles = (T + 15) >> 4, nkb = (T + 63) >> 6;        // 16-query blocks, 64-key blocks
-    if constexpr (NKB > 0) {
-        // ---- single pass, NKB = nkb key blocks: ALL scores of a query block stay in registers (32 NKB per thread and
-        //      block), so Q K^T is computed once -- the two-pass form below computes it twice, a third of the kernel's
-        //      mma.sync work.  Same arithmetic and rounding (global row maximum first).  With one CTA per SM this form
-        //      was slower (all warps in their mma-only and MUFU-only phases at the same time); with two to four
-        //      independent CTAs per SM the phases of different CTAs overlap.
-        constexpr int U = NKB <= 2 ? 2 : 1, NT = NKB * 8;
+    if constexpr (NT16 > 0) {
+        // ---- single pass over NT16 >= T / 16 sixteen-key steps: ALL scores of a query block stay in registers (8 NT16
+        //      per thread and block), so Q K^T is computed once -- the two-pass form below computes it twice, a third of
+        //      the kernel's mma.sync work -- and only for the keys that exist (T = 81: 96 instead of 128).  Same
+        //      arithmetic and rounding (global row maximum first).  With one CTA per SM this form was slower (all warps
+        //      in their mma-only and MUFU-only phases at the same time); with two to four independent CTAs per SM the
+        //      phases of different CTAs overlap.
+        constexpr int U = NT16 <= 8 ? 2 : 1, NT = NT16 * 2;
 #pragma unroll 1
         for (int mt0 = 0; mt0 < mtiles; mt0 += U) {
             uint32_t qa[U][4];
@@ -1636,7 +1637,7 @@ __global__ void __launch_bounds__(128, MINB) long_attention_kernel(const ModPara
 #pragma unroll
             for (int u = 0; u < U; ++u) {
 #pragma unroll
-                for (int nt = NT - 8; nt < NT; ++nt)                  // only the last key block holds keys past the end
+                for (int nt = NT - 4; nt < NT; ++nt)                  // only the last 32 keys can lie past the end
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         if (nt * 8 + t4 * 2 + (i & 1) >= T) s[u][nt][i] = -INFINITY;
@@ -1658,29 +1659,26 @@ __global__ void __launch_bounds__(128, MINB) long_attention_kernel(const ModPara
                     for (int i = 0; i < 4; ++i) o[u][dn][i] = 0.f;
             }
 #pragma unroll
-            for (int kblk = 0; kblk < NKB; ++kblk) {
+            for (int ks = 0; ks < NT16; ++ks) {
 #pragma unroll
                 for (int u = 0; u < U; ++u)
 #pragma unroll
-                    for (int nt = kblk * 8; nt < kblk * 8 + 8; ++nt) {
+                    for (int nt = 2 * ks; nt < 2 * ks + 2; ++nt) {
                         s[u][nt][0] = ex2_approx(fmaf(s[u][nt][0], scale, nm0[u])), s[u][nt][1] = ex2_approx(fmaf(s[u][nt][1], scale, nm0[u]));
                         s[u][nt][2] = ex2_approx(fmaf(s[u][nt][2], scale, nm1[u])), s[u][nt][3] = ex2_approx(fmaf(s[u][nt][3], scale, nm1[u]));
                         l0[u] += s[u][nt][0] + s[u][nt][1];
                         l1[u] += s[u][nt][2] + s[u][nt][3];
                     }
+                uint32_t vf[4];
+                ldsm_x4_t(vb + la_off(16 * ks + (mi & 1) * 8 + r8, 2 * h + (mi >> 1)), vf);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    uint32_t vf[4];
-                    ldsm_x4_t(vb + la_off(kblk * 64 + 16 * ks + (mi & 1) * 8 + r8, 2 * h + (mi >> 1)), vf);
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const int n0 = kblk * 8 + 2 * ks;
-                        uint32_t pa[4];
-                        pa[0] = pack_bf16(s[u][n0][0], s[u][n0][1]), pa[1] = pack_bf16(s[u][n0][2], s[u][n0][3]);
-                        pa[2] = pack_bf16(s[u][n0 + 1][0], s[u][n0 + 1][1]), pa[3] = pack_bf16(s[u][n0 + 1][2], s[u][n0 + 1][3]);
-                        mma_bf16_16816(o[u][0], pa, vf[0], vf[1]);
-                        mma_bf16_16816(o[u][1], pa, vf[2], vf[3]);
-                    }
+                for (int u = 0; u < U; ++u) {
+                    const int n0 = 2 * ks;
+                    uint32_t pa[4];
+                    pa[0] = pack_bf16(s[u][n0][0], s[u][n0][1]), pa[1] = pack_bf16(s[u][n0][2], s[u][n0][3]);
+                    pa[2] = pack_bf16(s[u][n0 + 1][0], s[u][n0 + 1][1]), pa[3] = pack_bf16(s[u][n0 + 1][2], s[u][n0 + 1][3]);
+                    mma_bf16_16816(o[u][0], pa, vf[0], vf[1]);
+                    mma_bf16_16816(o[u][1], pa, vf[2], vf[3]);
                 }
             }
             __syncwarp();
@@ -1853,16 +1851,21 @@ static int launch_long(ModParams p, int kind, void* scratch, size_t scratch_byte
     }
     if ((rc = cuda_status())) return rc;
     const int la_bytes = 3 * (int)la_rows(p.T) * 128;
-#define KASF_LA(MINB, NKB)                                                                                     \
+#define KASF_LA(MINB, NT16)                                                                                    \
     do {                                                                                                       \
-        cudaFuncSetAttribute(long_attention_kernel<MINB, NKB>, cudaFuncAttributeMaxDynamicSharedMemorySize, la_bytes); \
-        long_attention_kernel<MINB, NKB><<<2 * seqs, 128, la_bytes, st>>>(p);                                 \
+        cudaFuncSetAttribute(long_attention_kernel<MINB, NT16>, cudaFuncAttributeMaxDynamicSharedMemorySize, la_bytes); \
+        long_attention_kernel<MINB, NT16><<<2 * seqs, 128, la_bytes, st>>>(p);                                \
     } while (0)
-    const int nkb = (p.T + 63) >> 6;
-    if (nkb == 4) KASF_LA(2, 4);
-    else if (nkb == 3) KASF_LA(2, 3);
-    else if (nkb == 2) KASF_LA(3, 2);
-    else KASF_LA(4, 0);
+    const int nt16 = (p.T + 15) >> 4;                    // sixteen-key steps; instantiated: 5, 6, 7, 8, 10, 12, 14, 16
+    if (nt16 <= 4) KASF_LA(4, 0);                        // (T <= 64 never takes the split path: two-pass fallback)
+    else if (nt16 == 5) KASF_LA(3, 5);
+    else if (nt16 == 6) KASF_LA(3, 6);
+    else if (nt16 == 7) KASF_LA(3, 7);
+    else if (nt16 == 8) KASF_LA(3, 8);
+    else if (nt16 <= 10) KASF_LA(2, 10);
+    else if (nt16 <= 12) KASF_LA(2, 12);
+    else if (nt16 <= 14) KASF_LA(2, 14);
+    else KASF_LA(2, 16);
 #undef KASF_LA
     if ((rc = cuda_status())) return rc;
     return kind == KASF_KIND_ATTENTION ? launch_one<KASF_KIND_ATTENTION, KASF_MODE_LONG, 0>(p, st)

@@ -84,7 +84,10 @@ def _module_oracle(state, cfg, layer, br, kind, mode, v, XL, emulate):
 MODULES = [("att", "attention"), ("graph", "graph"), ("bone", "bone")]
 
 
-@pytest.mark.parametrize("T,B", [(27, 3), (27, 10), (9, 5), (81, 2), (128, 1), (100, 2), (243, 1), (243, 2), (150, 2)])
+# temporal split path: T = 72 / 81 / 100 / 128 / 150 / 185 / 215 / 243 cover every instantiated key-step count of the
+# attention core (5, 6, 7, 8, 10, 12, 14, 16 sixteen-key steps) and both M-tile counts of the GCN kernel
+@pytest.mark.parametrize("T,B", [(27, 3), (27, 10), (9, 5), (81, 2), (128, 1), (100, 2), (243, 1), (243, 2), (150, 2),
+                                 (72, 1), (185, 1), (215, 1)])
 @pytest.mark.parametrize("mode", ["spatial", "temporal"])
 @pytest.mark.parametrize("br,kind", MODULES)
 def test_former_module(br, kind, mode, T, B):
