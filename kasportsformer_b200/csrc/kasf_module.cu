@@ -94,7 +94,7 @@ constexpr uint32_t TM_HS = 384;
 // MMAK / MMAV (self-attention): K / V are in tensor memory -- they are drained to shared memory while the next
 // projection runs (one barrier each: a waiter may lag at most one phase behind an mbarrier).
 enum { B_FULL0 = 0, B_EMPTY0 = RING, B_AREADY = 2 * RING, B_MMA, B_HFULL0, B_HFULL1, B_HSREADY0, B_HSREADY1,
-       B_HSFREE0, B_HSFREE1, B_OUT, B_ROWS, B_MMAK, B_MMAV, B_LIMBFULL, B_A0FREE, B_OUTDONE, B_COUNT };
+       B_HSFREE0, B_HSFREE1, B_OUT, B_ROWS, B_MMAK, B_MMAV, B_LIMBFULL, B_A0FREE, B_OUTDONE, B_HFREE0, B_HFREE1, B_COUNT };
 static_assert(B_COUNT * 8 + 8 <= 256, "barrier block");
 
 struct ModParams {
@@ -788,7 +788,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
     if (tid == 0) {
         if ((smem_u32(sm) & 1023u) != 0) __trap();
         for (int i = 0; i < B_COUNT; ++i) {
-            const bool by_warps = i == B_AREADY || i == B_HSREADY0 || i == B_HSREADY1;
+            const bool by_warps = i == B_AREADY || i == B_HSREADY0 || i == B_HSREADY1 || i == B_HFREE0 || i == B_HFREE1;
             mbar_init(&bars[i], (by_warps || i == B_OUTDONE) ? CW : (i == B_ROWS ? CW * 32 * 2 : 1));   // ROWS: two half gathers
         }
         fence_mbar_init();
@@ -848,7 +848,7 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
         } else if (warp == W_MMA && lane == 0) {
             // ---- the only thread that issues tcgen05.mma
             const uint32_t a0_addr = smem_u32(sm + SM_A0), a1_addr = smem_u32(sm + SM_A1), ring_addr = smem_u32(sm + SM_RING);
-            uint32_t cslot = 0, cph = 0, ph_a = 0, ph_hs0 = 0, ph_hs1 = 0, ph_limb = 0;
+            uint32_t cslot = 0, cph = 0, ph_a = 0, ph_hs0 = 0, ph_hs1 = 0, ph_limb = 0, ph_hf = 0;
             auto chunk = [&](uint32_t tcol, uint32_t a_smem, bool acc, bool fp16_operands = false) {
                 mbar_wait(&bars[B_FULL0 + cslot], cph);
                 tc_fence_after();
@@ -922,14 +922,20 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
                     const int buf = c & 1;
-                    if (buf) { mbar_wait(&bars[B_HSREADY1], ph_hs1); ph_hs1 ^= 1; }
-                    else { mbar_wait(&bars[B_HSREADY0], ph_hs0); ph_hs0 ^= 1; }
-                    tc_fence_after();
-                    if (c < 2) {                               // fc1 chunk c+2 first: the epilogue warps wait for it
+                    if (c < 2) {
+                        // fc1 chunk c+2 as soon as every warp has READ accumulator c (a few hundred cycles into its GELU
+                        // epilogue), not when the epilogue is finished: fc2 of chunk c then follows its HSREADY directly,
+                        // and the hidden-operand buffer it frees is what the epilogue of chunk c+2 waits for
+                        mbar_wait(&bars[buf ? B_HFREE1 : B_HFREE0], ph_hf);
+                        tc_fence_after();
                         chunk(buf ? TM_H1 : TM_H0, a0_addr, false);
                         tc_commit(&bars[buf ? B_HFULL1 : B_HFULL0]);
                         if (c == 1 && limb_tiles) tc_commit(&bars[B_A0FREE]);   // last reader of the A tile
                     }
+                    if (buf) { mbar_wait(&bars[B_HSREADY1], ph_hs1); ph_hs1 ^= 1; }
+                    else { mbar_wait(&bars[B_HSREADY0], ph_hs0); ph_hs0 ^= 1; }
+                    tc_fence_after();
+                    if (c == 1) ph_hf ^= 1;
                     chunk_ts(TM_OUT, tmem + TM_HS + buf * 64, c > 0);                          // fc2: fp16 x fp16
                     if (c < 3) tc_commit(&bars[buf ? B_HSFREE1 : B_HSFREE0]);   // (c == 2: B1 is free for the next tile's rows)
                     if (c == 3) tc_commit(&bars[B_OUT]);
@@ -1240,6 +1246,10 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 tmem_ld32(e.tbase + (buf ? TM_H1 : TM_H0) + e.half * 64, acc[0]);
                 tmem_ld32(e.tbase + (buf ? TM_H1 : TM_H0) + e.half * 64 + 32, acc[1]);
                 tmem_ld_wait();
+                if (c < 2) {                                   // accumulator c is in registers: fc1 of chunk c+2 may overwrite it
+                    tc_fence_before();
+                    warp_arrive(&bars[buf ? B_HFREE1 : B_HFREE0], lane);
+                }
                 PMARK(15);
                 // two-stage software pipeline over groups of 8 columns: the tanh arguments of group g+1 are computed
                 // while the MUFU results of group g are in flight (the compiler's own schedule consumed each result
