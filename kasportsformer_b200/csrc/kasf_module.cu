@@ -964,6 +964,14 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
         }                                                             \
     } while (0)
 
+#ifdef KASF_STAGGER
+        {   // experiment: de-synchronise the SMs (equal tiles keep all 148 in the same phase: bursts on L2 / HBM)
+            const long long t0 = clock64();
+            const long long d = (long long)(blockIdx.x & 7) * KASF_STAGGER;
+            while (clock64() - t0 < d) {}
+            pt0 = PROF ? clock64() : 0;
+        }
+#endif
         gather_rows<MODE>(p, sm, blockIdx.x, first_src, &bars[B_ROWS], warp, lane, 0);
         gather_rows<MODE>(p, sm, blockIdx.x, first_src, &bars[B_ROWS], warp, lane, 1);
         if (limb_tiles && lane == 0) mbar_arrive(&bars[B_OUTDONE]);   // no previous tile: the accumulator columns are free
@@ -1319,33 +1327,58 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
             wt.wait(B_OUT);
             tc_fence_after();
             PMARK(16);
-            // ---- out = x1 + ls2 * (acc + b2): 256-bit stores of this thread's 64 columns, straight from registers
-            //      (staging the rows in shared memory for coalesced 128-bit stores was measured slower: 4.4k vs 3.4k
-            //       cycles per tile, the extra CTA barriers and the second pass over the data cost more than the LSU saves)
+            // ---- out = x1 + ls2 * (acc + b2).  The four lanes of a quad own four rows; a 4 x 4 transpose of their 8-float
+            //      pieces (two xor-shuffle stages) lets the quad write ONE 128-byte line per store instruction (8 lines of
+            //      4 sectors per warp instruction) instead of 32 lines of one sector each.  Measured (scripts/micro/
+            //      stg_patterns.cu): 3.94k cycles per 64 KB tile for the thread-per-row pattern on a single SM, 2.04k for
+            //      line-per-quad, 0.39k for the shuffles.  (Staging the rows in shared memory for coalesced stores was
+            //      slower than either: the extra CTA barriers and the second pass over the data cost more than they save.)
             {
-                float* orow = p.out + (tok >= 0 ? tok : 0) * D + e.half * 64;
+                const int s4 = lane & 3;
+                long long tokr[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) tokr[r] = __shfl_sync(0xffffffffu, tok, (lane & ~3) + r);
 #pragma unroll
                 for (int b = 0; b < 2; ++b) {
                     uint32_t acc[32];
                     tmem_ld32(e.tbase + TM_OUT + e.half * 64 + b * 32, acc);
                     tmem_ld_wait();
                     const float* xr = xv + b * 32;         // x1, in registers since the mixer epilogue
+                    float o[4][8];                         // piece c8 = columns 8 c8 .. 8 c8 + 7 of this block
 #pragma unroll
                     for (int c8 = 0; c8 < 4; ++c8) {
                         const int col = e.half * 64 + b * 32 + c8 * 8;
-                        float o[8];
 #pragma unroll
                         for (int h4 = 0; h4 < 2; ++h4) {
                             const float4 ls = *reinterpret_cast<const float4*>(vec + V_LS2 + col + h4 * 4);
                             const float4 b2 = *reinterpret_cast<const float4*>(vec + V_B2 + col + h4 * 4);
                             const int i = c8 * 8 + h4 * 4;
-                            o[h4 * 4 + 0] = fmaf(ls.x, __uint_as_float(acc[i + 0]) + b2.x, xr[i + 0]);
-                            o[h4 * 4 + 1] = fmaf(ls.y, __uint_as_float(acc[i + 1]) + b2.y, xr[i + 1]);
-                            o[h4 * 4 + 2] = fmaf(ls.z, __uint_as_float(acc[i + 2]) + b2.z, xr[i + 2]);
-                            o[h4 * 4 + 3] = fmaf(ls.w, __uint_as_float(acc[i + 3]) + b2.w, xr[i + 3]);
+                            o[c8][h4 * 4 + 0] = fmaf(ls.x, __uint_as_float(acc[i + 0]) + b2.x, xr[i + 0]);
+                            o[c8][h4 * 4 + 1] = fmaf(ls.y, __uint_as_float(acc[i + 1]) + b2.y, xr[i + 1]);
+                            o[c8][h4 * 4 + 2] = fmaf(ls.z, __uint_as_float(acc[i + 2]) + b2.z, xr[i + 2]);
+                            o[c8][h4 * 4 + 3] = fmaf(ls.w, __uint_as_float(acc[i + 3]) + b2.w, xr[i + 3]);
                         }
-                        if (tok >= 0) stg256(orow + b * 32 + c8 * 8, o);
                     }
+                    // transpose among the quad: afterwards o[r] = piece s4 of the row owned by lane (quad base + r)
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)            // stage xor 2: o[i + 2] of lanes 0,1 <-> o[i] of lanes 2,3
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const float send = (s4 & 2) ? o[i][k] : o[i + 2][k];
+                            const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+                            if (s4 & 2) o[i][k] = recv; else o[i + 2][k] = recv;
+                        }
+#pragma unroll
+                    for (int i = 0; i < 4; i += 2)         // stage xor 1: o[i + 1] of even lanes <-> o[i] of odd lanes
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const float send = (s4 & 1) ? o[i][k] : o[i + 1][k];
+                            const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+                            if (s4 & 1) o[i][k] = recv; else o[i + 1][k] = recv;
+                        }
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        if (tokr[r] >= 0) stg256(p.out + tokr[r] * D + e.half * 64 + b * 32 + s4 * 8, o[r]);
                 }
             }
             if (limb_tiles) warp_arrive(&bars[B_OUTDONE], lane);   // fc2 accumulator drained: V of the next tile may land
