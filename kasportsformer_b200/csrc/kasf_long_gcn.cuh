@@ -373,8 +373,9 @@ __global__ void __launch_bounds__(128 * MT + 32, MT == 1 ? 2 : 1) long_gcn_tc_ke
     mbar_wait(&bars[B_AGG + mt], 0);
     tc_fence_after();
     mark(5);
+    // (line-per-quad stores, quad_transpose8: the four lanes of a quad write one 128-byte line of one row per instruction)
     const long long R = seq * T + row;
-    __nv_bfloat16* dst = p.sq + R * D;
+    __nv_bfloat16* qbase = p.sq + (seq * T + (row & ~3)) * D;
 #pragma unroll 1
     for (int c = 0; c < 4; c += 2) {
         uint32_t va[32], vb[32];
@@ -382,19 +383,19 @@ __global__ void __launch_bounds__(128 * MT + 32, MT == 1 ? 2 : 1) long_gcn_tc_ke
         tmem_ld32(tb + 128 + (c + 1) * 32, vb);
         tmem_ld_wait32(va);
         tmem_ld_wait32(vb);
-        if (row < T) {
+        uint32_t w[4][8];                                  // 64 columns = 128 bytes = four 32-byte pieces
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint32_t w[8];
+        for (int q = 0; q < 4; ++q)
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int k = (q & 1) * 16 + 2 * i;
-                    w[i] = q < 2 ? pack_bf16(di * __uint_as_float(va[k]), di * __uint_as_float(va[k + 1]))
-                                 : pack_bf16(di * __uint_as_float(vb[k]), di * __uint_as_float(vb[k + 1]));
-                }
-                stg256u(dst + c * 32 + q * 16, w);
+            for (int i = 0; i < 8; ++i) {
+                const int k = (q & 1) * 16 + 2 * i;
+                w[q][i] = q < 2 ? pack_bf16(di * __uint_as_float(va[k]), di * __uint_as_float(va[k + 1]))
+                                : pack_bf16(di * __uint_as_float(vb[k]), di * __uint_as_float(vb[k + 1]));
             }
-        }
+        quad_transpose8(w, lane);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if ((row & ~3) + r < T) stg256u(qbase + r * D + c * 32 + (lane & 3) * 16, w[r]);
     }
     if (row < T) p.srow[R] = rs;
     mark(6);

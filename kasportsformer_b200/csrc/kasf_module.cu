@@ -1486,7 +1486,10 @@ __global__ void __launch_bounds__(256, 1) long_pre_kernel(const ModParams p) {
         const int next = tile + (int)gridDim.x;
         const long long R = (long long)tile * 128 + e.row;
         auto drain = [&](int qkv) {
-            __nv_bfloat16* dst = (qkv == 0 ? p.sq : (qkv == 1 ? p.sk : p.sv)) + R * D + e.half * 64;
+            // this thread's 64 columns as four 32-byte pieces of bf16 pairs; after the quad transpose the four lanes of
+            // a quad write one 128-byte line (the half row of ONE row) per instruction
+            __nv_bfloat16* base = (qkv == 0 ? p.sq : (qkv == 1 ? p.sk : p.sv)) + ((long long)tile * 128 + (e.row & ~3)) * D + e.half * 64;
+            uint32_t w[4][8];
 #pragma unroll
             for (int b = 0; b < 2; ++b) {
                 uint32_t acc[32];
@@ -1497,17 +1500,17 @@ __global__ void __launch_bounds__(256, 1) long_pre_kernel(const ModParams p) {
                     for (int i = 0; i < 32; ++i)
                         acc[i] = __float_as_uint(__uint_as_float(acc[i]) + vec[V_BQ + e.half * 64 + b * 32 + i]);
                 }
-                if (row_ok) {
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        uint32_t w[8];
+                for (int c = 0; c < 2; ++c)
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            w[i] = pack_bf16(__uint_as_float(acc[c * 16 + 2 * i]), __uint_as_float(acc[c * 16 + 2 * i + 1]));
-                        stg256u(dst + b * 32 + c * 16, w);
-                    }
-                }
+                    for (int i = 0; i < 8; ++i)
+                        w[b * 2 + c][i] = pack_bf16(__uint_as_float(acc[c * 16 + 2 * i]), __uint_as_float(acc[c * 16 + 2 * i + 1]));
             }
+            quad_transpose8(w, lane);
+            const int nrows_t = tile_rows<KASF_MODE_LONG>(p, tile);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if ((e.row & ~3) + r < nrows_t) stg256u(base + r * D + (lane & 3) * 16, w[r]);
         };
         if (KIND == KASF_KIND_BONE) {
             if (lt) {

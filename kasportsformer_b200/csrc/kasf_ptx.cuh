@@ -112,6 +112,30 @@ __device__ __forceinline__ void stg256u(void* p, const uint32_t (&v)[8]) {
                  : "memory");
 }
 
+// 4 x 4 transpose of 8-word pieces among the four lanes of a quad (two xor-shuffle stages): before, o[c] is piece c of
+// the row this lane owns; after, o[r] is piece (lane & 3) of the row owned by lane (quad base + r).  The quad can then
+// store ONE contiguous 128-byte line of row r per instruction (8 lines x 4 sectors per warp instruction) instead of 32
+// single sectors of 32 different lines: 2.0k instead of 3.9k cycles per 64 KB on one SM (scripts/micro/stg_patterns.cu).
+__device__ __forceinline__ void quad_transpose8(uint32_t (&o)[4][8], int lane) {
+    const int s4 = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t send = (s4 & 2) ? o[i][k] : o[i + 2][k];
+            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 2);
+            if (s4 & 2) o[i][k] = recv; else o[i + 2][k] = recv;
+        }
+#pragma unroll
+    for (int i = 0; i < 4; i += 2)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t send = (s4 & 1) ? o[i][k] : o[i + 1][k];
+            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+            if (s4 & 1) o[i][k] = recv; else o[i + 1][k] = recv;
+        }
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {  // one full warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
