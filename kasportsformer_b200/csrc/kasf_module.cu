@@ -1008,6 +1008,14 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 warp_arrive(&bars[B_AREADY], lane);
                 PMARK(0);
             }
+            // split path: this row's mixer-core output (bf16, scratch) is requested first, its latency runs under the
+            // staged-row reads and the tensor-memory stores
+            uint4 pre8[8];
+            if (POST) {
+                const uint4* src = reinterpret_cast<const uint4*>(p.sq + ((long long)tile * 128 + e.row) * D + e.half * 64);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) pre8[c] = row_ok ? __ldg(src + c) : make_uint4(0u, 0u, 0u, 0u);
+            }
             // ---- residual rows: staging -> registers -> tensor memory (resident); LN1 -> A operand
             wt.wait(B_ROWS);
             PMARK(13);
@@ -1021,12 +1029,9 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
             }
             if (POST && KIND != KASF_KIND_GRAPH) {
                 // ---- split path: the attention output of this tile's rows (bf16, scratch) is the A operand
-                const uint4* src = reinterpret_cast<const uint4*>(p.sq + ((long long)tile * 128 + e.row) * D + e.half * 64);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint4 o8 = row_ok ? __ldg(src + c) : make_uint4(0u, 0u, 0u, 0u);
-                    *reinterpret_cast<uint4*>(sm + SM_A0 + tile_off_bf16(e.row, e.half * 64 + c * 8)) = o8;
-                }
+                for (int c = 0; c < 8; ++c)
+                    *reinterpret_cast<uint4*>(sm + SM_A0 + tile_off_bf16(e.row, e.half * 64 + c * 8)) = pre8[c];
             } else {
                 ln_stats_merge(sm, e, xv, mean, rstd, ln_flip);
                 if (KIND == KASF_KIND_BONE) {
@@ -1121,9 +1126,8 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                 uint4 agg8[8];                             // split path: A_hat z of this row (bf16) from scratch
                 if (POST) {
                     const long long R = (long long)tile * 128 + e.row;
-                    const uint4* src = reinterpret_cast<const uint4*>(p.sq + R * D + e.half * 64);
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) agg8[c] = row_ok ? __ldg(src + c) : make_uint4(0u, 0u, 0u, 0u);
+                    for (int c = 0; c < 8; ++c) agg8[c] = pre8[c];
                     rs = row_ok ? __ldg(p.srow + R) : 0.f;
                 }
 #pragma unroll
