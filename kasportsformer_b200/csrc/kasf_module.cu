@@ -346,12 +346,95 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // overwrites the Q block it consumed.  U independent items are interleaved per warp to hide the
 // ldmatrix -> mma -> shuffle -> ex2 -> mma dependency chain.  GS > 0: the group size is a compile-time
 // constant (17 joints), so key tiles past the group and the key masks fold away.
+// The 17th joint of a spatial group.  17 query rows are one full 16-row MMA block plus ONE row, and a second block for
+// that row costs as much as the first (half of the spatial attention core, 3.4k cycles per tile).  Here the 56
+// (group, head) leftover queries of a tile go to the CUDA cores instead, four lanes each (eight pairs per warp and
+// round, seven rounds per tile): a lane takes the keys s, s+4, .. of the group (dot products over the 16 head
+// dimensions, bf16 operands from shared memory, fp32 accumulation), maximum and sum are reduced over the quad, P is
+// rounded to bf16 as in the MMA path, P V is reduced with a transpose-reduce (8 + 4 shuffles) that leaves every lane
+// with four finished output dimensions.  (Eight lanes per pair, to balance the warps in half-rounds, was slower: 7.0k
+// instead of 6.5k cycles for attention core + projection wait; the second MMA block cost 8.0k.)
+__device__ __forceinline__ void attention_row16(uint8_t* sm, int round, int lane, int nrows) {
+    const int pair = round * 8 + (lane >> 2), s4 = lane & 3;
+    const int g = pair >> 3, h = pair & 7;
+    const bool live = (g + 1) * J <= nrows;
+    const int gr0 = live ? g * J : 0, qrow = gr0 + J - 1;
+    const float scale = 0.25f * 1.4426950408889634f;
+    auto unpack16 = [](const uint4& a, const uint4& b, float (&f)[16]) {
+        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[2 * i] = __uint_as_float(w[i] << 16), f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    };
+    float q[16];
+    unpack16(*reinterpret_cast<const uint4*>(sm + SM_A0 + tile_off_bf16(qrow, h * DH)),
+             *reinterpret_cast<const uint4*>(sm + SM_A0 + tile_off_bf16(qrow, h * DH + 8)), q);
+    float sc[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const int key = s4 + 4 * i;                        // (i == 4: key 16, lane 0 of the quad only)
+        const int krow = gr0 + min(key, J - 1);
+        float k[16];
+        unpack16(*reinterpret_cast<const uint4*>(sm + SM_KV + f32_off(krow, 2 * h)),
+                 *reinterpret_cast<const uint4*>(sm + SM_KV + f32_off(krow, 2 * h + 1)), k);
+        float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; c += 2) d0 = fmaf(q[c], k[c], d0), d1 = fmaf(q[c + 1], k[c + 1], d1);
+        sc[i] = key < J ? d0 + d1 : -INFINITY;
+    }
+    float mx = fmaxf(fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3])), sc[4]);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    const float nm = -mx * scale;
+    float l = 0.f, o[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) o[c] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const int key = s4 + 4 * i;
+        const int krow = gr0 + min(key, J - 1);
+        const float pf = ex2_approx(fmaf(sc[i], scale, nm));          // (masked key: ex2(-inf) = 0)
+        l += pf;
+        const float pb = __uint_as_float(pack_bf16(pf, 0.f) << 16);   // P rounded to bf16, as the MMA operand is
+        float v[16];
+        unpack16(*reinterpret_cast<const uint4*>(sm + SM_KV + f32_off(krow, 16 + 2 * h)),
+                 *reinterpret_cast<const uint4*>(sm + SM_KV + f32_off(krow, 16 + 2 * h + 1)), v);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) o[c] = fmaf(pb, v[c], o[c]);
+    }
+    l += __shfl_xor_sync(0xffffffffu, l, 1);
+    l += __shfl_xor_sync(0xffffffffu, l, 2);
+    // transpose-reduce over the quad: after xor 2 a lane holds 8 dimensions (summed over two lanes), after xor 1 four
+    float r8[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float send = (s4 & 2) ? o[c] : o[c + 8];
+        const float keep = (s4 & 2) ? o[c + 8] : o[c];
+        r8[c] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    float r4[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float send = (s4 & 1) ? r8[c] : r8[c + 4];
+        const float keep = (s4 & 1) ? r8[c + 4] : r8[c];
+        r4[c] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+    const int d0 = ((s4 >> 1) << 3) + ((s4 & 1) << 2);    // this lane's four dimensions
+    const float inv = rcp_approx(l);
+    __syncwarp();                                          // every lane of the quad has read q before it is overwritten
+    if (live) {
+        uint2 pk;
+        pk.x = pack_bf16(r4[0] * inv, r4[1] * inv), pk.y = pack_bf16(r4[2] * inv, r4[3] * inv);
+        *reinterpret_cast<uint2*>(sm + SM_A0 + tile_off_bf16(qrow, h * DH + d0)) = pk;
+    }
+}
+
 template <int MAXNT, int U, int GS>   // MAXNT: key tiles of 8 held in registers (gsize <= 8 * MAXNT)
 __device__ __forceinline__ void attention_core_impl(uint8_t* sm, int warp, int lane, int gsize_rt, int nrows) {
     const uint32_t q_base = smem_u32(sm + SM_A0), kv_base = smem_u32(sm + SM_KV);
     const int gsize = GS ? GS : gsize_rt;
     const int ngroups = nrows / gsize;
-    const int mtiles = (gsize + 15) >> 4;
+    // 17-joint groups: one 16-query block on the tensor cores, the 17th query on the CUDA cores (attention_row16)
+    const int mtiles = GS == J ? 1 : (gsize + 15) >> 4;
     const int nkt = (gsize + 7) >> 3;                             // key tiles that hold keys of the group
     const int items = ngroups * HEADS * mtiles;
     // item / mtiles by multiplication (items < 1024, mtiles <= 8: exact); a runtime integer division per item and
@@ -494,7 +577,13 @@ __device__ __forceinline__ void attention_core_impl(uint8_t* sm, int warp, int l
 #endif
 template <int MODE, int TC>
 __device__ __forceinline__ void attention_core(uint8_t* sm, int warp, int lane, int gsize, int nrows) {
-    if (MODE == KASF_MODE_SPATIAL) attention_core_impl<4, KASF_ATT_U_S, J>(sm, warp, lane, gsize, nrows);
+    if (MODE == KASF_MODE_SPATIAL) {
+        attention_core_impl<4, KASF_ATT_U_S, J>(sm, warp, lane, gsize, nrows);
+        // seven rounds of 8 (group, head) pairs, one per warp 1..7.  (Measured: an MMA round of four items costs 2.1k
+        // cycles, a round here 2.3k; warps 0-5 have two MMA rounds, warps 6, 7 one.  Two rounds for warps 6, 7 and one for
+        // warps 3-5 was slower: 6.9k instead of 6.5k cycles for attention core + projection wait.)
+        if (warp >= 1) attention_row16(sm, 7 - warp, lane, nrows);
+    }
     else if (TC == 0) attention_core_impl<4, KASF_ATT_U_T0, 0>(sm, warp, lane, gsize, nrows);
     else if (TC == 1) attention_core_impl<8, 2, 0>(sm, warp, lane, gsize, nrows);
     else attention_core_impl<16, 1, 0>(sm, warp, lane, gsize, nrows);
