@@ -442,15 +442,18 @@ __device__ __forceinline__ void attention_core_impl(uint8_t* sm, int warp, int l
     const uint32_t inv_mtiles = (65536u + (uint32_t)mtiles - 1u) / (uint32_t)mtiles;
     const int g8 = lane >> 2, t4 = lane & 3, mi = lane >> 3, r8 = lane & 7;
     const float scale = 0.25f * 1.4426950408889634f;              // head_dim^-1/2 * log2(e)
+    // every warp takes a contiguous, equally long range of items (spatial: 56 items = 7 per warp, i.e. a round of four
+    // and a round of three; a round-robin over rounds of U gave six warps eight items and two warps four)
+    const int ipw = (items + CW - 1) / CW, it_end = min(items, (warp + 1) * ipw);
 #pragma unroll 1
-    for (int it0 = warp * U; it0 < items; it0 += CW * U) {
+    for (int it0 = warp * ipw; it0 < it_end; it0 += U) {
         int h[U], gr0[U], mt[U];
         bool live[U];
         uint32_t qa[U][4];
         float s[U][MAXNT][4];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            live[u] = it0 + u < items;
+            live[u] = it0 + u < it_end;
             const int item = live[u] ? it0 + u : it0;
             const int gh = GS ? item / mtiles : (int)(((uint32_t)item * inv_mtiles) >> 16);
             mt[u] = item - gh * mtiles, h[u] = gh & (HEADS - 1);
