@@ -1428,7 +1428,12 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
             //      4 sectors per warp instruction) instead of 32 lines of one sector each.  Measured (scripts/micro/
             //      stg_patterns.cu): 3.94k cycles per 64 KB tile for the thread-per-row pattern on a single SM, 2.04k for
             //      line-per-quad, 0.39k for the shuffles.  (Staging the rows in shared memory for coalesced stores was
-            //      slower than either: the extra CTA barriers and the second pass over the data cost more than they save.)
+            //      slower than either: the extra CTA barriers and the second pass over the data cost more than they save.
+            //      Keeping the finished rows in registers and issuing these stores in the NEXT tile, behind its LN1
+            //      hand-over where the warps wait 2.2k cycles for the Q|K|V MMAs, moved 2.0k cycles of stores under
+            //      that wait and won nothing: the wait shrank by 0.75k and the LN / drain / attention phases that
+            //      followed grew by as much -- the stores drain through the same load/store pipeline as the
+            //      shared-memory traffic of those phases.  25.3k vs 25.2k cycles per tile, bone modules 4 % slower.)
             {
                 const int s4 = lane & 3;
                 long long tokr[4];
