@@ -1355,6 +1355,9 @@ __global__ void __launch_bounds__(MOD_THREADS, 1) former_module_kernel(const Mod
                     warp_arrive(&bars[buf ? B_HFREE1 : B_HFREE0], lane);
                 }
                 PMARK(15);
+                // (bias + polynomial of two of the eight groups on the fp32 FMA pipe instead of in packed half, to relieve
+                //  the half-rate fp16 pipe, was measured slower: 5.7k instead of 5.4k cycles per tile, 14.2k vs 14.5k clips/s
+                //  -- the loop is bound by issue slots and dependent chains, not by that pipe)
                 // two-stage software pipeline over groups of 8 columns: the tanh arguments of group g+1 are computed
                 // while the MUFU results of group g are in flight (the compiler's own schedule consumed each result
                 // a few instructions after issuing it: 1960 vs 1440 cycles per chunk, scripts/micro/gelu_epi.cu)
