@@ -108,3 +108,23 @@ def test_procrustes_routine_host(lib):
         a = lib.kasf_selftest_p_mpjpe_host(p.ctypes.data, t.ctypes.data)
         b = MO.p_mpjpe(p[None], t[None])[0]
         assert abs(a - b) <= 1e-9 * max(1.0, abs(b)), (case, a, b)
+
+
+def test_launch_counts_and_passes(lib):
+    """Host-side accounting of a forward (no GPU): 186 launches on the fused path; temporal modules of sequences
+    longer than 64 frames take the split path (3 / 2 / 3 kernels instead of 1 per temporal module: 316 launches);
+    a batch that does not fit the 3 GiB of streams is split into EQUAL passes (256 clips at T = 243: 2 x 128)."""
+    def cfg(T):
+        return dict(CFG, n_frames=T)
+    assert _capi.forward_launches(cfg(27), 1024) == 1 + 2 + 26 * 7 + 1
+    assert _capi.forward_launches(cfg(64), 16) == 1 + 2 + 26 * 7 + 1
+    assert _capi.forward_launches(cfg(81), 256) == 1 + 2 + 26 * 12 + 1
+    assert _capi.forward_launches(cfg(243), 128) == 1 + 2 + 26 * 12 + 1
+    assert _capi.forward_launches(cfg(243), 256) == 2 * (1 + 2 + 26 * 12 + 1)
+    # equal passes: the workspace of 256 clips at T = 243 is the one of 128 clips, not of 253
+    assert _capi.workspace_bytes(cfg(243), 256) == _capi.workspace_bytes(cfg(243), 128)
+    assert _capi.workspace_bytes(cfg(243), 128) > _capi.workspace_bytes(cfg(243), 64)
+    # the split path needs scratch and limb tiles in (sequence, frame) order; the fused path no scratch
+    c81, c27 = _capi.c_config(cfg(81)), _capi.c_config(cfg(27))
+    assert lib.kasf_module_scratch_bytes(C.byref(c81), 4) > 0 and lib.kasf_module_scratch_bytes(C.byref(c27), 4) == 0
+    assert lib.kasf_limb_tiles_bytes(C.byref(c81), 4, 1) == ((4 * 17 * 81 + 127) // 128) * 32768
